@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the vector-search hot path (BASELINE.json metric).
+
+Workload (config.workload): IVF-Flat, L2, N = 1M x 768 float32 per GPU, nlist = 1024 per GPU, nprobe = 32,
+batch = 1024 queries per GPU, top-10 — BASELINE.json configs[1] at the batch size the metric is quoted on.
+A "step" is one batched search (b200vs_search) over synthetic U[0,1) vectors.
+
+  value : QPS with queries / results resident in HBM (b200vs_search_device), CUDA events, max over ranks.
+  e2e   : QPS through the host-pointer C-ABI call (b200vs_search) with pinned host buffers: H2D of the queries
+          and D2H of (dist, id) inside the timed region.
+  roofline : the list-scan kernel's algorithmic bytes (rows of the distinct probed lists x (d*4+8))
+          / its CUDA-event duration (library profiling mode, separate pass) vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline : the CPU oracle (restated reference path, AVX-512 order) on the box's host cores, bounded sample.
+
+Multi-GPU (torchrun, one rank per GPU): the index is sharded BY INVERTED LIST: centroids are
+replicated, every rank scans the probed lists it owns for the whole (N x 1024)-query batch, then ONE
+all_gather of the per-shard top-k over NCCL + the on-GPU k-way merge kernel.  Weak scaling: per-GPU database
+and per-GPU batch are fixed.
+
+--impl reference : times the reference's CPU implementation of the same path (the oracle port; faiss itself is
+not vendored in /root/reference) with all host threads, rank 0 only.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "dingo-store_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200vs", choices=["b200vs", "reference"])
+    ap.add_argument("--nb", type=int, default=1_000_000, help="database vectors per GPU")
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--nlist", type=int, default=1024, help="inverted lists per GPU")
+    ap.add_argument("--nprobe", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=1024, help="queries per GPU per step")
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exact-only", action="store_true", help="force the exact FP32 scan path")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gen_chunks(torch, n, d, seed, device, chunk=131072):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    for a in range(0, n, chunk):
+        m = min(chunk, n - a)
+        yield a, torch.rand((m, d), generator=g, device=device, dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle with every host thread (rank 0 only)
+# --------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle_lib
+    o = oracle_lib.load()
+    cores = os.cpu_count() or 1
+    n, d, nlist = args.nb, args.dim, args.nlist
+    rng = np.random.default_rng(1234)
+    xb = rng.random((n, d), dtype=np.float32)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    t0 = time.time()
+    # training sample as faiss would take it (<= 256 points per centroid); fewer when the host is small so the
+    # whole arm stays within minutes — the index SHAPE (nlist, list lengths) is what the timed search depends on
+    max_pts = 256 if cores >= 32 else 64
+    niter = 10 if cores >= 32 else 4
+    cent = o.kmeans(oracle_lib.L2, xb[: min(n, nlist * max_pts)], nlist, niter=niter, max_pts=max_pts, nthreads=cores)
+    asg = o.assign(oracle_lib.L2, xb, cent, nthreads=cores)
+    order = np.argsort(asg, kind="stable")
+    off = np.zeros(nlist + 1, np.int64)
+    off[1:] = np.cumsum(np.bincount(asg, minlength=nlist))
+    lx, lids = xb[order], ids[order]
+    del xb
+    build_s = time.time() - t0
+    xq = np.random.default_rng(4321).random((args.batch, d), dtype=np.float32)
+    # calibrate a bounded sample: ~2 s of CPU work per step
+    t = time.time()
+    o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq[: cores], args.k, args.nprobe, nthreads=cores)
+    per_q = (time.time() - t) / cores
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    sample = int(max(cores, min(args.batch, (min(2.0, budget) / max(per_q, 1e-6)))))
+    for _ in range(args.warmup):
+        o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq[:sample], args.k, args.nprobe, nthreads=cores)
+    t = time.time()
+    for _ in range(args.steps):
+        o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq[:sample], args.k, args.nprobe, nthreads=cores)
+    el = time.time() - t
+    qps = sample * args.steps / el
+    line = {"impl": "reference", "metric": "QPS at batch-1024 top-10 dim=768; recall@10 vs ref; % HBM roofline", "value": qps,
+            "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} of the {args.batch}-query batch per step, {cores} threads, one query per task; "
+                                       f"oracle port of the reference path (faiss not vendored); index built on CPU in {build_s:.0f}s "
+                                       f"(kmeans niter={niter}, {max_pts} pts/centroid)"},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"IVF-Flat L2 {args.nb}x{args.dim} f32 per GPU, nlist={args.nlist} per GPU, nprobe={args.nprobe}, "
+                        f"batch={args.batch} per GPU, top-{args.k} (BASELINE configs[1] at the metric's batch 1024)",
+            "index": "IVF_FLAT", "metric_type": "L2", "nb_per_gpu": args.nb, "dim": args.dim, "nlist_per_gpu": args.nlist,
+            "nprobe": args.nprobe, "batch_per_gpu": args.batch, "topk": args.k,
+            "parallelism": f"list-sharded x{world}, 1 all_gather + merge" if world > 1 else "single GPU",
+            "l2_flush": "inputs larger than L2: every step streams the probed lists (~3.1 GB per GPU >> 126 MB L2)"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import b200vs
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, d, nlist_local, k = args.nb, args.dim, args.nlist, args.k
+    nlist = nlist_local * world
+    nq = args.batch * world
+    t_build = time.time()
+
+    # ---- build: synthetic data, train, (multi-GPU: exchange rows to their list owners), add ----
+    ix = b200vs.Index(b200vs.IVF_FLAT, b200vs.L2, d, nlist=nlist, device=local_rank)
+    chunks = [(a, x.cpu().numpy()) for a, x in gen_chunks(torch, n, d, 1234 + rank, dev)]
+    ntrain = min(n, nlist_local * 256)
+    train = np.concatenate([c for _, c in chunks], 0)[:ntrain] if len(chunks) > 1 else chunks[0][1][:ntrain]
+    if world == 1:
+        ix.train(train)
+        for a, x in chunks:
+            for b in range(0, x.shape[0], 32768):  # kBuildVectorIndexBatchSize, src/common/constant.h:173
+                ix.add(x[b:b + 32768], np.arange(a + b + 1, a + b + 1 + min(32768, x.shape[0] - b), dtype=np.int64))
+    else:
+        # local k-means -> global centroid table (replicated); rows go to the rank that owns their list
+        loc = b200vs.Index(b200vs.IVF_FLAT, b200vs.L2, d, nlist=nlist_local, device=local_rank)
+        loc.train(train)
+        cent_local = torch.from_numpy(loc.get_trained_state()[32:].view(np.float32).reshape(nlist_local, d).copy()).to(dev)
+        loc.close()
+        cent_all = [torch.empty_like(cent_local) for _ in range(world)]
+        dist.all_gather(cent_all, cent_local)
+        cent = torch.cat(cent_all, 0).cpu().numpy()
+        ix.set_trained_state(b200vs.ivf_state_blob(cent, b200vs.L2))
+        cq = b200vs.Index(b200vs.FLAT, b200vs.L2, d, device=local_rank)  # coarse quantiser as a Flat index over centroids
+        cq.add(cent, np.arange(nlist, dtype=np.int64))
+        for a, x in chunks:
+            _, lst = cq.search(x, 1)
+            owner = torch.from_numpy((lst[:, 0] // nlist_local).astype(np.int64))
+            order = torch.argsort(owner, stable=True)
+            counts = torch.bincount(owner, minlength=world)
+            xs = torch.from_numpy(x)[order].to(dev)
+            gid = (torch.arange(a + 1, a + 1 + x.shape[0], dtype=torch.int64) + rank * n)[order].to(dev)
+            rc = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_to_all_single(rc, counts.to(dev))
+            rcl, scl = rc.tolist(), counts.tolist()
+            xr = torch.empty((sum(rcl), d), dtype=torch.float32, device=dev)
+            ir = torch.empty(sum(rcl), dtype=torch.int64, device=dev)
+            dist.all_to_all_single(xr, xs, rcl, scl)
+            dist.all_to_all_single(ir, gid, rcl, scl)
+            xr, ir = xr.cpu().numpy(), ir.cpu().numpy()
+            for b in range(0, xr.shape[0], 32768):
+                ix.add(xr[b:b + 32768], ir[b:b + 32768])
+        cq.close()
+    del chunks, train
+    build_s = time.time() - t_build
+
+    # ---- query batches (all ranks hold the same global batch) ----
+    gq = torch.Generator(device=dev)
+    gq.manual_seed(4321)
+    nbatches = 4
+    q_dev = [torch.rand((nq, d), generator=gq, device=dev, dtype=torch.float32) for _ in range(nbatches)]
+    out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    sp, _keep = b200vs.make_search_params(nprobe=args.nprobe, exact_only=args.exact_only)
+    stream = torch.cuda.current_stream()
+    if world > 1:
+        g_d = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
+        g_i = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+        m_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        m_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+
+    launches = [0]
+
+    def step_device(i):
+        q = q_dev[i % nbatches]
+        ix.search_device(nq, q.data_ptr(), k, out_d.data_ptr(), out_i.data_ptr(), stream=stream.cuda_stream, sp=sp)
+        launches[0] += ix.stats()[0]
+        if world > 1:
+            dist.all_gather_into_tensor(g_d.view(-1), out_d.view(-1))
+            dist.all_gather_into_tensor(g_i.view(-1), out_i.view(-1))
+            b200vs.merge_topk_device(local_rank, world, nq, k, g_d.data_ptr(), g_i.data_ptr(), m_d.data_ptr(), m_i.data_ptr(), stream.cuda_stream)
+            launches[0] += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step_device(i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    gpu_launches = launches[0]
+
+    # ---- e2e: host buffers through the public C-ABI call, copies inside the timed region ----
+    q_host = [q.cpu().pin_memory() for q in q_dev]
+    hd = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    hi = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    if world > 1:
+        hd_all = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        q = q_host[i % nbatches]
+        if world == 1:
+            ix.search_raw(nq, q.data_ptr(), k, hd.data_ptr(), hi.data_ptr(), sp=sp)
+            return float(hd[0, 0])
+        qd = q.to(dev, non_blocking=True)
+        ix.search_device(nq, qd.data_ptr(), k, out_d.data_ptr(), out_i.data_ptr(), stream=stream.cuda_stream, sp=sp)
+        dist.all_gather_into_tensor(g_d.view(-1), out_d.view(-1))
+        dist.all_gather_into_tensor(g_i.view(-1), out_i.view(-1))
+        b200vs.merge_topk_device(local_rank, world, nq, k, g_d.data_ptr(), g_i.data_ptr(), m_d.data_ptr(), m_i.data_ptr(), stream.cuda_stream)
+        hd_all.copy_(m_d, non_blocking=True)
+        hi.copy_(m_i, non_blocking=True)
+        torch.cuda.synchronize()
+        return float(hd_all[0, 0])
+
+    for i in range(max(3, args.warmup)):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t.tolist()
+    else:
+        e2e_ms = e2e_s * 1e3
+    qps = nq * args.steps / (ms / 1e3)
+    e2e_qps = nq * args.steps / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant kernel (separate, profiled pass; never part of the timed numbers) ----
+    ix.set_profiling(True)
+    kt, rows = [], 0
+    for i in range(3):
+        ix.search_device(nq, q_dev[i % nbatches].data_ptr(), k, out_d.data_ptr(), out_i.data_ptr(), stream=stream.cuda_stream, sp=sp)
+        torch.cuda.synchronize()
+        st = ix.stats()
+        kt.append(st[3] / 1e9)
+        rows = st[4]
+    ix.set_profiling(False)
+    peak, how = measured_peaks()
+    kern_s = float(np.mean(kt)) if kt and min(kt) > 0 else None
+    alg_bytes = rows * (d * 4 + 8)
+    roofline = {"bound": "hbm", "achieved": (alg_bytes / kern_s / 1e9) if kern_s else None, "peak": peak, "unit": "GB/s",
+                "frac": (alg_bytes / kern_s / 1e9 / peak) if kern_s else None, "traffic": None,
+                "kernel": "ivf list scan", "kernel_ms": kern_s * 1e3 if kern_s else None,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)" if how == "measured" else "fallback 6650 GB/s"}
+
+    # ---- cpu_baseline: the oracle on the host cores, bounded sample (rank 0, N = 1 only) ----
+    cpu_baseline = None
+    recall_vs_oracle = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle_lib
+        o = oracle_lib.load()
+        cores = os.cpu_count() or 1
+        off, lx, _, lids = ix.export_lists(nlist)
+        cent = ix.get_trained_state()[32:].view(np.float32).reshape(nlist, d)
+        xq = q_host[0].numpy()
+        t = time.time()
+        o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq[:cores], k, args.nprobe, nthreads=cores)
+        per_q = (time.time() - t) / cores
+        sample = args.cpu_sample or int(max(cores, min(nq, 15.0 / max(per_q, 1e-6))))
+        t = time.time()
+        Do, Io = o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq[:sample], k, args.nprobe, nthreads=cores)
+        cpu_s = time.time() - t
+        ix.search_raw(nq, q_host[0].data_ptr(), k, hd.data_ptr(), hi.data_ptr(), sp=sp)
+        Ig, Dg = hi.numpy()[:sample], hd.numpy()[:sample]
+        recall_vs_oracle = float(np.mean([len(set(a) & set(b)) / k for a, b in zip(Ig, Io)]))
+        ids_exact = bool(np.array_equal(Ig, Io))
+        cpu_baseline = {"value": sample / cpu_s, "unit": "queries/s", "cores": cores, "kind": "port",
+                        "sample": f"first {sample} queries of the {nq}-query batch on the same trained index, {cores} threads, one query per task",
+                        "recall_at_k_gpu_vs_oracle": recall_vs_oracle, "ids_bit_exact": ids_exact,
+                        "max_rel_dist_err": float(np.max(np.abs(Dg - Do) / np.maximum(np.abs(Do), 1e-12)))}
+
+    if rank == 0:
+        line = {"metric": "QPS at batch-1024 top-10 dim=768; recall@10 vs ref; % HBM roofline", "value": qps, "unit": "queries/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, world),
+                "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 12,
+                        "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "recall_at_10_vs_oracle": recall_vs_oracle, "build_seconds": build_s, "search_stats": ix.stats()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,276 @@
+// api.cu — extern "C" entry points of libb200vs.so (declared in include/b200vs.h).
+// No exception leaves this file: every entry point maps failures to a b200vs_status
+// (reference convention: butil::Status codes, never exceptions across the plugin virtual;
+// src/vector/vector_index_flat.cc:313-315, src/handler/raft_apply_handler.cc:1311-1325).
+#include <cstdio>
+#include <new>
+
+#include "index.h"
+
+using namespace b200vs;
+
+struct b200vs_index {
+  IndexBase* impl;
+};
+
+namespace {
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    return f();
+  } catch (const StatusError& e) {
+    g_last_error = e.msg;
+    return e.code;
+  } catch (const CudaError& e) {
+    g_last_error = e.what();
+    return B200VS_EINTERNAL;
+  } catch (const std::bad_alloc&) {
+    g_last_error = "out of host memory";
+    return B200VS_EINTERNAL;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return B200VS_EINTERNAL;
+  } catch (...) {
+    g_last_error = "unknown error";
+    return B200VS_EINTERNAL;
+  }
+}
+
+IndexBase* get(b200vs_index* h) {
+  if (!h || !h->impl) fail(B200VS_EILLEGAL_PARAMETERS, "null index handle");
+  return h->impl;
+}
+
+// resolve search params; uploads the sorted id list into scratch (stream-ordered)
+SearchCtx make_ctx(IndexBase* ix, const b200vs_search_params* sp, cudaStream_t s) {
+  SearchCtx sc;
+  if (!sp) return sc;
+  sc.nprobe = sp->nprobe;
+  sc.efsearch = sp->efsearch;
+  sc.exact_only = sp->exact_only;
+  sc.has_range = sp->has_range;
+  sc.negate = sp->negate;
+  sc.rmin = sp->range_min;
+  sc.rmax = sp->range_max;
+  if (sp->sorted_ids) {
+    long long* d = ix->scratch.alloc<long long>((size_t)std::max<int64_t>(sp->n_ids, 1));
+    if (sp->n_ids > 0) B200VS_CUDA(cudaMemcpyAsync(d, sp->sorted_ids, (size_t)sp->n_ids * 8, cudaMemcpyHostToDevice, s));
+    sc.sorted_ids_dev = d;
+    sc.n_ids = sp->n_ids;
+  }
+  return sc;
+}
+
+void check_search_args(IndexBase* ix, int64_t nq, const float* xq, const b200vs_search_params* sp) {
+  if (nq <= 0 || !xq) fail(B200VS_EILLEGAL_PARAMETERS, "vector_with_ids is empty");  // flat.cc:208-210
+  if (ix->type == B200VS_HNSW && sp && (sp->efsearch < 0 || sp->efsearch > 1024))
+    fail(B200VS_EILLEGAL_PARAMETERS, "efsearch is illegal, " + std::to_string(sp->efsearch) + ", must between 0 and 1024");  // hnsw.cc:332-336
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200vs_create(b200vs_type type, b200vs_metric metric, int32_t dim, const b200vs_params* params, b200vs_index** out) {
+  return guarded([&]() -> int {
+    if (!out) fail(B200VS_EILLEGAL_PARAMETERS, "out is null");
+    *out = nullptr;
+    if (dim <= 0) fail(B200VS_EILLEGAL_PARAMETERS, "dimension must be > 0");
+    if (metric != B200VS_L2 && metric != B200VS_IP && metric != B200VS_COSINE) fail(B200VS_EILLEGAL_PARAMETERS, "unsupported metric type");
+    b200vs_params p;
+    memset(&p, 0, sizeof(p));
+    if (params) p = *params;
+    int ndev = 0;
+    B200VS_CUDA(cudaGetDeviceCount(&ndev));
+    if (p.device < 0 || p.device >= ndev) fail(B200VS_EILLEGAL_PARAMETERS, "bad CUDA device ordinal");
+    IndexBase* impl = nullptr;
+    switch (type) {
+      case B200VS_FLAT: impl = make_flat(metric, dim, p); break;
+      case B200VS_IVF_FLAT: impl = make_ivf_flat(metric, dim, p); break;
+      case B200VS_IVF_PQ: impl = make_ivf_pq(metric, dim, p); break;
+      case B200VS_HNSW: impl = make_hnsw(metric, dim, p); break;
+      default: fail(B200VS_EILLEGAL_PARAMETERS, "unknown index type");
+    }
+    *out = new b200vs_index{impl};
+    return B200VS_OK;
+  });
+}
+
+void b200vs_destroy(b200vs_index* h) {
+  if (!h) return;
+  try { delete h->impl; } catch (...) {}
+  delete h;
+}
+
+int b200vs_train(b200vs_index* h, int64_t n, const float* x) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    if (n <= 0 || !x) fail(B200VS_EILLEGAL_PARAMETERS, "data size invalid");  // ivf_flat.cc:646-649
+    ix->train(n, x);
+    return B200VS_OK;
+  });
+}
+
+int b200vs_set_trained_state(b200vs_index* h, const void* blob, size_t len) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    if (!blob) fail(B200VS_EILLEGAL_PARAMETERS, "null blob");
+    ix->set_state(blob, len);
+    return B200VS_OK;
+  });
+}
+
+int64_t b200vs_get_trained_state(b200vs_index* h, void* blob, size_t cap) {
+  int64_t r = 0;
+  int rc = guarded([&]() -> int { r = get(h)->get_state(blob, cap); return B200VS_OK; });
+  return rc == B200VS_OK ? r : -(int64_t)rc;
+}
+
+int b200vs_add_with_ids(b200vs_index* h, int64_t n, const float* x, const int64_t* ids, int upsert) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    if (n <= 0 || !x || !ids) fail(B200VS_EILLEGAL_PARAMETERS, "vector_with_ids is empty");  // flat.cc:123-125
+    ix->add(n, x, ids, upsert != 0);
+    return B200VS_OK;
+  });
+}
+
+int b200vs_remove_ids(b200vs_index* h, int64_t n, const int64_t* ids, int64_t* n_removed) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    if (n_removed) *n_removed = 0;
+    if (n <= 0) return B200VS_OK;  // "delete_ids.empty() -> OK", flat.cc:172-174
+    if (!ids) fail(B200VS_EILLEGAL_PARAMETERS, "null ids");
+    const int64_t r = ix->remove(n, ids);
+    if (n_removed) *n_removed = r < 0 ? 0 : r;
+    // IVF types: "remove not found vector id" -> EVECTOR_INVALID (ivf_flat.cc:180-184); untrained -> OK (r == -1)
+    if (r == 0 && (ix->type == B200VS_IVF_FLAT || ix->type == B200VS_IVF_PQ)) fail(B200VS_EVECTOR_INVALID, "remove not found vector id");
+    return B200VS_OK;
+  });
+}
+
+int b200vs_search_device(b200vs_index* h, int64_t nq, const float* xq_dev, int32_t k, const b200vs_search_params* sp,
+                         float* out_dist_dev, int64_t* out_ids_dev, void* stream) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    check_search_args(ix, nq, xq_dev, sp);
+    if (k <= 0) return B200VS_OK;  // "topk <= 0 -> OK", flat.cc:212
+    if (!out_ids_dev) fail(B200VS_EILLEGAL_PARAMETERS, "null output");
+    std::shared_lock<std::shared_mutex> rl(ix->rw);
+    std::lock_guard<std::mutex> gl(ix->gpu_mu);
+    ix->set_device();
+    cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
+    if (s != ix->last_stream) { B200VS_CUDA(cudaStreamSynchronize(ix->last_stream)); ix->last_stream = s; }
+    ix->scratch.reset(s);
+    for (int i = 0; i < 8; ++i) ix->stats[i] = 0;
+    SearchCtx sc = make_ctx(ix, sp, s);
+    ix->search_dev(nq, xq_dev, k, sc, out_dist_dev, (long long*)out_ids_dev, s);
+    return B200VS_OK;
+  });
+}
+
+int b200vs_search(b200vs_index* h, int64_t nq, const float* xq, int32_t k, const b200vs_search_params* sp, float* out_dist,
+                  int64_t* out_ids) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    check_search_args(ix, nq, xq, sp);
+    if (k <= 0) return B200VS_OK;
+    if (!out_ids || !out_dist) fail(B200VS_EILLEGAL_PARAMETERS, "null output");
+    std::shared_lock<std::shared_mutex> rl(ix->rw);
+    std::lock_guard<std::mutex> gl(ix->gpu_mu);
+    ix->set_device();
+    cudaStream_t s = ix->stream;
+    if (s != ix->last_stream) { B200VS_CUDA(cudaStreamSynchronize(ix->last_stream)); ix->last_stream = s; }
+    ix->scratch.reset(s);
+    for (int i = 0; i < 8; ++i) ix->stats[i] = 0;
+    float* dq = ix->scratch.alloc<float>((size_t)nq * ix->dim);
+    float* dd = ix->scratch.alloc<float>((size_t)nq * k);
+    long long* di = ix->scratch.alloc<long long>((size_t)nq * k);
+    B200VS_CUDA(cudaMemcpyAsync(dq, xq, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice, s));
+    SearchCtx sc = make_ctx(ix, sp, s);
+    ix->search_dev(nq, dq, k, sc, dd, di, s);
+    B200VS_CUDA(cudaMemcpyAsync(out_dist, dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
+    B200VS_CUDA(cudaMemcpyAsync(out_ids, di, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s));
+    B200VS_CUDA(cudaStreamSynchronize(s));
+    return B200VS_OK;
+  });
+}
+
+int b200vs_range_search(b200vs_index* h, int64_t nq, const float* xq, float radius, int32_t max_results,
+                        const b200vs_search_params* sp, float* out_dist, int64_t* out_ids, int32_t* out_counts) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    check_search_args(ix, nq, xq, sp);
+    if (ix->type == B200VS_HNSW) fail(B200VS_EVECTOR_NOT_SUPPORT, "RangeSearch not support in Hnsw!!!");  // hnsw.cc:487-493
+    if (max_results <= 0 || !out_ids || !out_dist || !out_counts) fail(B200VS_EILLEGAL_PARAMETERS, "bad range-search outputs");
+    std::shared_lock<std::shared_mutex> rl(ix->rw);
+    std::lock_guard<std::mutex> gl(ix->gpu_mu);
+    ix->set_device();
+    cudaStream_t s = ix->stream;
+    if (s != ix->last_stream) { B200VS_CUDA(cudaStreamSynchronize(ix->last_stream)); ix->last_stream = s; }
+    ix->scratch.reset(s);
+    float* dq = ix->scratch.alloc<float>((size_t)nq * ix->dim);
+    float* dd = ix->scratch.alloc<float>((size_t)nq * max_results);
+    long long* di = ix->scratch.alloc<long long>((size_t)nq * max_results);
+    int* dc = ix->scratch.alloc<int>((size_t)nq);
+    B200VS_CUDA(cudaMemcpyAsync(dq, xq, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice, s));
+    SearchCtx sc = make_ctx(ix, sp, s);
+    ix->range_search_dev(nq, dq, radius, max_results, sc, dd, di, dc, s);
+    B200VS_CUDA(cudaMemcpyAsync(out_dist, dd, (size_t)nq * max_results * 4, cudaMemcpyDeviceToHost, s));
+    B200VS_CUDA(cudaMemcpyAsync(out_ids, di, (size_t)nq * max_results * 8, cudaMemcpyDeviceToHost, s));
+    B200VS_CUDA(cudaMemcpyAsync(out_counts, dc, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    B200VS_CUDA(cudaStreamSynchronize(s));
+    return B200VS_OK;
+  });
+}
+
+int b200vs_count(b200vs_index* h, int64_t* count) {
+  return guarded([&]() -> int { IndexBase* ix = get(h); std::shared_lock<std::shared_mutex> rl(ix->rw); if (count) *count = ix->count(); return B200VS_OK; });
+}
+int b200vs_deleted_count(b200vs_index* h, int64_t* count) {
+  return guarded([&]() -> int { IndexBase* ix = get(h); std::shared_lock<std::shared_mutex> rl(ix->rw); if (count) *count = ix->deleted_count(); return B200VS_OK; });
+}
+int b200vs_memory_size(b200vs_index* h, int64_t* bytes) {
+  return guarded([&]() -> int { IndexBase* ix = get(h); std::shared_lock<std::shared_mutex> rl(ix->rw); if (bytes) *bytes = ix->memory_size(); return B200VS_OK; });
+}
+int b200vs_is_trained(b200vs_index* h) {
+  int r = 0;
+  guarded([&]() -> int { IndexBase* ix = get(h); std::shared_lock<std::shared_mutex> rl(ix->rw); r = ix->is_trained() ? 1 : 0; return B200VS_OK; });
+  return r;
+}
+int32_t b200vs_dimension(b200vs_index* h) { return h && h->impl ? h->impl->dim : -1; }
+
+int b200vs_save(b200vs_index* h, const char* path) {
+  return guarded([&]() -> int { if (!path) fail(B200VS_EILLEGAL_PARAMETERS, "null path"); get(h)->save(path); return B200VS_OK; });
+}
+int b200vs_load(b200vs_index* h, const char* path) {
+  return guarded([&]() -> int { if (!path) fail(B200VS_EILLEGAL_PARAMETERS, "null path"); get(h)->load(path); return B200VS_OK; });
+}
+
+int b200vs_export_lists(b200vs_index* h, int64_t* list_off, float* vectors, uint8_t* codes, int64_t* ids) {
+  return guarded([&]() -> int { get(h)->export_lists(list_off, vectors, codes, ids); return B200VS_OK; });
+}
+
+int b200vs_merge_topk_device(int32_t device, int32_t nparts, int64_t nq, int32_t k, const float* parts_dist,
+                             const int64_t* parts_ids, float* out_dist, int64_t* out_ids, void* stream) {
+  return guarded([&]() -> int {
+    if (nparts <= 0 || nq <= 0 || k <= 0 || !parts_dist || !parts_ids || !out_dist || !out_ids) fail(B200VS_EILLEGAL_PARAMETERS, "bad merge arguments");
+    B200VS_CUDA(cudaSetDevice(device));
+    launch_merge_api(nparts, nq, k, parts_dist, (const long long*)parts_ids, out_dist, (long long*)out_ids, (cudaStream_t)stream);
+    return B200VS_OK;
+  });
+}
+
+int b200vs_last_search_stats(b200vs_index* h, int64_t stats[8]) {
+  return guarded([&]() -> int { IndexBase* ix = get(h); for (int i = 0; i < 8; ++i) stats[i] = ix->stats[i]; return B200VS_OK; });
+}
+
+int b200vs_set_profiling(b200vs_index* h, int on) {
+  return guarded([&]() -> int { get(h)->profiling = on != 0; return B200VS_OK; });
+}
+
+const char* b200vs_last_error(void) { return g_last_error.c_str(); }
+const char* b200vs_version(void) { return "b200vs 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,496 @@
+// index.cu — IndexBase, FlatIndex, IvfFlatIndex (device-resident replacements of the faiss objects held by
+// VectorIndexFlat / VectorIndexIvfFlat, src/vector/vector_index_flat.cc:73-107, vector_index_ivf_flat.cc:805-837).
+#include <algorithm>
+#include <cstdio>
+#include <random>
+#include <unordered_set>
+
+#include "index.h"
+#include "ivf_common.h"
+
+namespace b200vs {
+
+thread_local std::string g_last_error;
+
+IndexBase::IndexBase(b200vs_type t, b200vs_metric m, int d, const b200vs_params& p)
+    : type(t), metric(m), dim(d), device(p.device), params(p) {
+  set_device();
+  B200VS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  last_stream = stream;
+}
+IndexBase::~IndexBase() {
+  cudaSetDevice(device);
+  if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+}
+
+const float* IndexBase::prepare_queries(int64_t nq, const float* xq_dev, cudaStream_t s) {
+  if (metric != B200VS_COSINE) return xq_dev;
+  float* q = scratch.alloc<float>((size_t)nq * dim);
+  if (type == B200VS_HNSW) {  // NormalizeVectorForHnsw, vector_index_hnsw.cc:449-452
+    launch_normalize_hnsw(xq_dev, q, nq, dim, s);
+  } else {                    // NormalizeVectorForFaiss via ExtractVectorValue(normalize_), flat.cc:243
+    B200VS_CUDA(cudaMemcpyAsync(q, xq_dev, (size_t)nq * dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    launch_normalize_faiss(q, nq, dim, s);
+  }
+  launch_count(1);
+  return q;
+}
+
+void IndexBase::save(const std::string&) { fail(B200VS_EVECTOR_NOT_SUPPORT, "save not supported for this index type"); }
+void IndexBase::load(const std::string&) { fail(B200VS_EVECTOR_NOT_SUPPORT, "load not supported for this index type"); }
+
+void check_batch_ids_unique(int64_t n, const int64_t* ids) {  // CheckVectorIdDuplicated, vector_index_utils.cc:551-561
+  std::unordered_set<int64_t> seen;
+  seen.reserve((size_t)n * 2);
+  for (int64_t i = 0; i < n; ++i)
+    if (!seen.insert(ids[i]).second) fail(B200VS_EVECTOR_ID_DUPLICATED, "vector id duplicated: " + std::to_string(ids[i]));
+}
+
+// ============================================================================================
+// Flat
+// ============================================================================================
+struct FlatIndex : IndexBase {
+  DevBuf<float> vecs;
+  DevBuf<long long> ids;
+  DevBuf<float> norms;
+  int64_t rows = 0;
+  std::vector<int64_t> h_ids;
+  std::unordered_map<int64_t, int64_t> id2row;
+  int64_t ndeleted = 0;
+
+  FlatIndex(b200vs_metric m, int d, const b200vs_params& p) : IndexBase(B200VS_FLAT, m, d, p) {}
+
+  void reserve_rows(int64_t need) {
+    if ((size_t)need * dim <= vecs.cap) return;
+    int64_t ncap = std::max<int64_t>(need, std::max<int64_t>(1024, (int64_t)(vecs.cap / dim) * 3 / 2));
+    vecs.reserve((size_t)ncap * dim, (size_t)rows * dim, stream);
+    ids.reserve((size_t)ncap, (size_t)rows, stream);
+    norms.reserve((size_t)ncap, (size_t)rows, stream);
+  }
+
+  void tombstone(const std::vector<int64_t>& rws) {
+    if (rws.empty()) return;
+    long long* d_rows = scratch.alloc<long long>(rws.size());
+    B200VS_CUDA(cudaMemcpyAsync(d_rows, rws.data(), rws.size() * 8, cudaMemcpyHostToDevice, stream));
+    launch_set_ids(ids.p, d_rows, (int64_t)rws.size(), -1, stream);
+    B200VS_CUDA(cudaStreamSynchronize(stream));
+    for (int64_t r : rws) h_ids[r] = -1;
+    ndeleted += (int64_t)rws.size();
+  }
+
+  void compact_if_needed() {
+    if (ndeleted == 0 || ndeleted * 2 < rows) return;
+    std::vector<long long> src, dst;
+    src.reserve(rows - ndeleted);
+    for (int64_t r = 0; r < rows; ++r) if (h_ids[r] >= 0) src.push_back(r);
+    const int64_t live = (int64_t)src.size();
+    dst.resize(live);
+    for (int64_t i = 0; i < live; ++i) dst[i] = i;
+    DevBuf<float> nv; DevBuf<long long> ni; DevBuf<float> nn;
+    const int64_t ncap = std::max<int64_t>(1024, live * 5 / 4);
+    nv.reserve((size_t)ncap * dim, 0, stream); ni.reserve(ncap, 0, stream); nn.reserve(ncap, 0, stream);
+    long long* d_src = scratch.alloc<long long>(live + 1);
+    long long* d_dst = scratch.alloc<long long>(live + 1);
+    if (live) {
+      B200VS_CUDA(cudaMemcpyAsync(d_src, src.data(), live * 8, cudaMemcpyHostToDevice, stream));
+      B200VS_CUDA(cudaMemcpyAsync(d_dst, dst.data(), live * 8, cudaMemcpyHostToDevice, stream));
+      launch_move_rows(vecs.p, ids.p, norms.p, d_src, d_dst, live, dim, nv.p, ni.p, nn.p, stream);
+    }
+    B200VS_CUDA(cudaStreamSynchronize(stream));
+    std::swap(vecs.p, nv.p); std::swap(vecs.cap, nv.cap);
+    std::swap(ids.p, ni.p); std::swap(ids.cap, ni.cap);
+    std::swap(norms.p, nn.p); std::swap(norms.cap, nn.cap);
+    std::vector<int64_t> nh(live);
+    id2row.clear();
+    for (int64_t i = 0; i < live; ++i) { nh[i] = h_ids[src[i]]; id2row[nh[i]] = i; }
+    h_ids.swap(nh);
+    rows = live; ndeleted = 0;
+  }
+
+  // VectorIndexFlat::AddOrUpsert, vector_index_flat.cc:121-162: duplicate ids inside the batch are rejected,
+  // pre-existing ids are ALWAYS removed first (add and upsert behave the same), then add_with_ids.
+  void add(int64_t n, const float* x, const int64_t* in_ids, bool) override {
+    check_batch_ids_unique(n, in_ids);
+    std::unique_lock<std::shared_mutex> wl(rw);
+    std::lock_guard<std::mutex> gl(gpu_mu);
+    set_device();
+    scratch.reset(stream);
+    std::vector<int64_t> dead;
+    for (int64_t i = 0; i < n; ++i) {
+      auto it = id2row.find(in_ids[i]);
+      if (it != id2row.end()) { dead.push_back(it->second); id2row.erase(it); }
+    }
+    tombstone(dead);
+    reserve_rows(rows + n);
+    float* st = scratch.alloc<float>((size_t)n * dim);
+    long long* st_ids = scratch.alloc<long long>(n);
+    long long* st_slots = scratch.alloc<long long>(n);
+    std::vector<long long> slots(n);
+    for (int64_t i = 0; i < n; ++i) slots[i] = rows + i;
+    B200VS_CUDA(cudaMemcpyAsync(st, x, (size_t)n * dim * 4, cudaMemcpyHostToDevice, stream));
+    B200VS_CUDA(cudaMemcpyAsync(st_ids, in_ids, (size_t)n * 8, cudaMemcpyHostToDevice, stream));
+    B200VS_CUDA(cudaMemcpyAsync(st_slots, slots.data(), (size_t)n * 8, cudaMemcpyHostToDevice, stream));
+    if (metric == B200VS_COSINE) launch_normalize_faiss(st, n, dim, stream);  // flat.cc:155 (normalize_)
+    launch_scatter_rows(st, st_ids, st_slots, n, dim, vecs.p, ids.p, norms.p, stream);
+    B200VS_CUDA(cudaStreamSynchronize(stream));
+    h_ids.resize(rows + n);
+    for (int64_t i = 0; i < n; ++i) { h_ids[rows + i] = in_ids[i]; id2row[in_ids[i]] = rows + i; }
+    rows += n;
+    compact_if_needed();
+  }
+
+  // VectorIndexFlat::Delete, vector_index_flat.cc:171-203: unknown ids are ignored (only ids present in
+  // rev_map are handed to remove_ids).
+  int64_t remove(int64_t n, const int64_t* del) override {
+    std::unique_lock<std::shared_mutex> wl(rw);
+    std::lock_guard<std::mutex> gl(gpu_mu);
+    set_device();
+    scratch.reset(stream);
+    std::vector<int64_t> dead;
+    for (int64_t i = 0; i < n; ++i) {
+      auto it = id2row.find(del[i]);
+      if (it != id2row.end()) { dead.push_back(it->second); id2row.erase(it); }
+    }
+    tombstone(dead);
+    compact_if_needed();
+    return (int64_t)dead.size();
+  }
+
+  ScanJob job(const SearchCtx& sc) const {
+    ScanJob j;
+    j.l2 = metric == B200VS_L2;
+    j.vecs = vecs.p; j.ids = ids.p; j.d = dim; j.mode = 0; j.n = rows; j.sc = &sc;
+    return j;
+  }
+
+  void search_dev(int64_t nq, const float* xq, int k, const SearchCtx& sc, float* od, long long* oi, cudaStream_t s) override {
+    const float* q = prepare_queries(nq, xq, s);
+    run_scan(this, job(sc), nq, q, k, od, nullptr, oi, nullptr, s);
+  }
+
+  // VectorIndexFlat::RangeSearch, vector_index_flat.cc:267-323: radius -> 1 - radius for IP / cosine (:282-285);
+  // faiss range_search keeps L2 dis < radius, IP ip > radius.
+  void range_search_dev(int64_t nq, const float* xq, float radius, int max_results, const SearchCtx& sc, float* od,
+                        long long* oi, int* oc, cudaStream_t s) override {
+    const float* q = prepare_queries(nq, xq, s);
+    ScanJob j = job(sc);
+    j.has_thr = true;
+    j.thr_raw = ip_like() ? 1.0F - radius : radius;
+    run_scan(this, j, nq, q, max_results, od, nullptr, oi, oc, s);
+  }
+
+  int64_t count() const override { return rows - ndeleted; }
+  int64_t deleted_count() const override { return ndeleted; }
+  int64_t memory_size() const override { return (int64_t)(vecs.cap * 4 + ids.cap * 8 + norms.cap * 4); }
+
+  void export_lists(int64_t* list_off, float* vectors, uint8_t*, int64_t* out_ids) override {
+    std::shared_lock<std::shared_mutex> rl(rw);
+    std::lock_guard<std::mutex> gl(gpu_mu);
+    set_device();
+    const int64_t live = rows - ndeleted;
+    if (list_off) { list_off[0] = 0; list_off[1] = live; }
+    std::vector<float> tmp;
+    if (vectors && ndeleted) tmp.resize((size_t)rows * dim);
+    if (vectors) {
+      float* dst = ndeleted ? tmp.data() : vectors;
+      B200VS_CUDA(cudaMemcpy(dst, vecs.p, (size_t)rows * dim * 4, cudaMemcpyDeviceToHost));
+    }
+    int64_t o = 0;
+    for (int64_t r = 0; r < rows; ++r) {
+      if (h_ids[r] < 0) continue;
+      if (out_ids) out_ids[o] = h_ids[r];
+      if (vectors && ndeleted) memcpy(vectors + (size_t)o * dim, tmp.data() + (size_t)r * dim, (size_t)dim * 4);
+      ++o;
+    }
+  }
+};
+
+IndexBase* make_flat(b200vs_metric m, int d, const b200vs_params& p) { return new FlatIndex(m, d, p); }
+
+// ============================================================================================
+// IVF arena shared by IVF-Flat (and reused by IVF-PQ for ids): see ivf_common.h
+// ============================================================================================
+
+struct IvfFlatIndex : IndexBase {
+  int nlist;            // may degenerate to 1 at train time (vector_index_ivf_flat.cc:676-680)
+  bool trained = false;
+  DevBuf<float> centroids;       // [nlist, d]
+  DevBuf<long long> cent_ids;    // iota
+  DevBuf<float> cent_norms;      // ||c||^2 (tensor-core coarse pass)
+  DevBuf<float> vecs;            // arena [arena_cap, d]
+  DevBuf<long long> ids;         // arena
+  DevBuf<float> norms;           // arena
+  IvfLists L;                    // host bookkeeping + device list_off/list_len
+
+  IvfFlatIndex(b200vs_metric m, int d, const b200vs_params& p) : IndexBase(B200VS_IVF_FLAT, m, d, p) {
+    nlist = p.nlist > 0 ? p.nlist : 2048;  // Constant::kCreateIvfFlatParamNcentroids
+  }
+  bool is_trained() const override { return trained; }
+
+  void install_centroids(const float* host_c, int k) {
+    nlist = k;
+    centroids.free(); cent_ids.free(); cent_norms.free();
+    centroids.reserve((size_t)k * dim, 0, stream);
+    cent_ids.reserve(k, 0, stream);
+    cent_norms.reserve(k, 0, stream);
+    B200VS_CUDA(cudaMemcpyAsync(centroids.p, host_c, (size_t)k * dim * 4, cudaMemcpyHostToDevice, stream));
+    launch_iota(cent_ids.p, k, stream);
+    B200VS_CUDA(cudaStreamSynchronize(stream));
+    L.init(k, stream);
+    vecs.free(); ids.free(); norms.free();
+    trained = true;
+  }
+
+  // trained-state blob: int64 hdr[4] = {magic 'IVFC', nlist, dim, metric}; float centroids[nlist*dim]
+  void set_state(const void* blob, size_t len) override {
+    std::unique_lock<std::shared_mutex> wl(rw);
+    std::lock_guard<std::mutex> gl(gpu_mu);
+    set_device();
+    if (len < 32) fail(B200VS_EILLEGAL_PARAMETERS, "state blob too short");
+    const int64_t* hdr = (const int64_t*)blob;
+    if (hdr[0] != 0x43465649 || hdr[2] != dim) fail(B200VS_EILLEGAL_PARAMETERS, "bad IVF state blob");
+    const int k = (int)hdr[1];
+    if (len < 32 + (size_t)k * dim * 4) fail(B200VS_EILLEGAL_PARAMETERS, "state blob truncated");
+    install_centroids((const float*)((const char*)blob + 32), k);
+  }
+  int64_t get_state(void* blob, size_t cap) override {
+    std::shared_lock<std::shared_mutex> rl(rw);
+    if (!trained) return 0;
+    const size_t need = 32 + (size_t)nlist * dim * 4;
+    if (!blob || cap < need) return (int64_t)need;
+    set_device();
+    int64_t hdr[4] = {0x43465649, nlist, dim, (int64_t)metric};
+    memcpy(blob, hdr, 32);
+    B200VS_CUDA(cudaMemcpy((char*)blob + 32, centroids.p, (size_t)nlist * dim * 4, cudaMemcpyDeviceToHost));
+    return (int64_t)need;
+  }
+
+  // assign rows (device, already normalised) to their nearest centroid: IndexFlat quantiser, k = 1
+  void assign_dev(const float* x_dev, int64_t n, long long* out_list_dev, cudaStream_t s) {
+    ScanJob j;
+    j.l2 = metric == B200VS_L2;
+    j.vecs = centroids.p; j.ids = cent_ids.p; j.d = dim; j.mode = 0; j.n = nlist;
+    const int64_t chunk = 32768;
+    for (int64_t a = 0; a < n; a += chunk) {
+      const int64_t m = std::min(chunk, n - a);
+      const size_t mark = scratch.used;
+      run_scan(this, j, m, x_dev + (size_t)a * dim, 1, nullptr, nullptr, out_list_dev + a, nullptr, s);
+      scratch.used = mark;  // stream-ordered reuse
+    }
+  }
+
+  // VectorIndexIvfFlat::Train, vector_index_ivf_flat.cc:644-712 -> faiss IndexIVFFlat::train ->
+  // Clustering (niter 10, seed 1234, <= 256 points per centroid); GPU Lloyd iterations here.
+  void train(int64_t n, const float* x) override;
+
+  void add(int64_t n, const float* x, const int64_t* in_ids, bool upsert) override;
+  int64_t remove(int64_t n, const int64_t* del) override;
+  int64_t remove_locked(int64_t n, const int64_t* del);
+  void maybe_compact();
+
+  int resolve_nprobe(const SearchCtx& sc) const {
+    int np = sc.nprobe > 0 ? sc.nprobe : 80;  // Constant::kSearchIvfFlatParamNprobe, ivf_flat.cc:211
+    return std::min(np, nlist);               // ivf_flat.cc:234
+  }
+
+  void search_dev(int64_t nq, const float* xq, int k, const SearchCtx& sc, float* od, long long* oi, cudaStream_t s) override;
+  void range_search_dev(int64_t nq, const float* xq, float radius, int max_results, const SearchCtx& sc, float* od,
+                        long long* oi, int* oc, cudaStream_t s) override;
+
+  long long* coarse(int64_t nq, const float* q, int nprobe, cudaStream_t s) {
+    ScanJob j;
+    j.l2 = metric == B200VS_L2;
+    j.vecs = centroids.p; j.ids = cent_ids.p; j.d = dim; j.mode = 0; j.n = nlist;
+    long long* probes = scratch.alloc<long long>((size_t)nq * nprobe);
+    run_scan(this, j, nq, q, nprobe, nullptr, nullptr, probes, nullptr, s);
+    return probes;
+  }
+  ScanJob list_job(const SearchCtx& sc, const long long* probes, int nprobe) const {
+    ScanJob j;
+    j.l2 = metric == B200VS_L2;
+    j.vecs = vecs.p; j.ids = ids.p; j.d = dim; j.mode = 1; j.probes = probes; j.nprobe = nprobe;
+    j.list_off = L.d_off.p; j.list_len = L.d_len.p; j.sc = &sc;
+    j.avg_candidates = nlist > 0 ? (double)L.total_len() * nprobe / nlist : 0;
+    return j;
+  }
+
+  int64_t count() const override { return L.live; }
+  int64_t deleted_count() const override { return L.dead; }
+  int64_t memory_size() const override {
+    return (int64_t)(vecs.cap * 4 + ids.cap * 8 + norms.cap * 4 + centroids.cap * 4);
+  }
+  void export_lists(int64_t* list_off, float* vectors, uint8_t*, int64_t* out_ids) override;
+};
+
+void IvfFlatIndex::train(int64_t n, const float* x) {
+  if (n <= 0) fail(B200VS_EILLEGAL_PARAMETERS, "data size invalid");
+  std::unique_lock<std::shared_mutex> wl(rw);
+  std::lock_guard<std::mutex> gl(gpu_mu);
+  if (trained) return;  // ivf_flat.cc:670-672
+  set_device();
+  scratch.reset(stream);
+  int k = nlist;
+  if (n < k) k = 1;  // "data size too small, nlist degenerate to 1", ivf_flat.cc:676-680
+  std::vector<float> cent;
+  kmeans_gpu(this, metric, dim, n, x, k, 10, 256, 1234, cent, [&](const float* xd, int64_t m, const float* cd, int kk, long long* out) {
+    // assignment against the CURRENT centroids cd (device)
+    ScanJob j;
+    j.l2 = metric == B200VS_L2;
+    j.vecs = cd; j.ids = cent_ids.p; j.d = dim; j.mode = 0; j.n = kk;
+    const int64_t chunk = 32768;
+    for (int64_t a = 0; a < m; a += chunk) {
+      const int64_t mm = std::min(chunk, m - a);
+      const size_t mark = scratch.used;
+      run_scan(this, j, mm, xd + (size_t)a * dim, 1, nullptr, nullptr, out + a, nullptr, stream);
+      scratch.used = mark;
+    }
+  }, [&](int kk) { cent_ids.free(); cent_ids.reserve(kk, 0, stream); launch_iota(cent_ids.p, kk, stream); });
+  install_centroids(cent.data(), k);
+}
+
+void IvfFlatIndex::add(int64_t n, const float* x, const int64_t* in_ids, bool upsert) {
+  std::unique_lock<std::shared_mutex> wl(rw);
+  if (!trained) fail(B200VS_EVECTOR_NOT_TRAIN, "not train");  // ivf_flat.cc:111-113 (caller trains and retries, :136-150)
+  std::lock_guard<std::mutex> gl(gpu_mu);
+  set_device();
+  scratch.reset(stream);
+  if (upsert) remove_locked(n, in_ids);  // ivf_flat.cc:115-118
+  float* st = scratch.alloc<float>((size_t)n * dim);
+  long long* st_ids = scratch.alloc<long long>(n);
+  long long* st_list = scratch.alloc<long long>(n);
+  long long* st_slots = scratch.alloc<long long>(n);
+  B200VS_CUDA(cudaMemcpyAsync(st, x, (size_t)n * dim * 4, cudaMemcpyHostToDevice, stream));
+  B200VS_CUDA(cudaMemcpyAsync(st_ids, in_ids, (size_t)n * 8, cudaMemcpyHostToDevice, stream));
+  if (metric == B200VS_COSINE) launch_normalize_faiss(st, n, dim, stream);
+  assign_dev(st, n, st_list, stream);
+  std::vector<long long> h_list(n), slots(n);
+  B200VS_CUDA(cudaMemcpyAsync(h_list.data(), st_list, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));
+  B200VS_CUDA(cudaStreamSynchronize(stream));
+  // host: reserve slots (may relocate lists / grow the arena)
+  std::vector<int> need(nlist, 0);
+  for (int64_t i = 0; i < n; ++i) need[h_list[i]]++;
+  L.reserve_for(need, [&](int64_t arena_rows) {
+    vecs.reserve((size_t)arena_rows * dim, (size_t)L.arena_used_before * dim, stream);
+    ids.reserve((size_t)arena_rows, (size_t)L.arena_used_before, stream);
+    norms.reserve((size_t)arena_rows, (size_t)L.arena_used_before, stream);
+  }, [&](int64_t src, int64_t dst, int64_t len) {
+    B200VS_CUDA(cudaMemcpyAsync(vecs.p + (size_t)dst * dim, vecs.p + (size_t)src * dim, (size_t)len * dim * 4, cudaMemcpyDeviceToDevice, stream));
+    B200VS_CUDA(cudaMemcpyAsync(ids.p + dst, ids.p + src, (size_t)len * 8, cudaMemcpyDeviceToDevice, stream));
+    B200VS_CUDA(cudaMemcpyAsync(norms.p + dst, norms.p + src, (size_t)len * 4, cudaMemcpyDeviceToDevice, stream));
+  });
+  for (int64_t i = 0; i < n; ++i) slots[i] = L.append((int)h_list[i], in_ids[i]);
+  B200VS_CUDA(cudaMemcpyAsync(st_slots, slots.data(), (size_t)n * 8, cudaMemcpyHostToDevice, stream));
+  launch_scatter_rows(st, st_ids, st_slots, n, dim, vecs.p, ids.p, norms.p, stream);
+  L.upload(stream);
+  B200VS_CUDA(cudaStreamSynchronize(stream));
+}
+
+int64_t IvfFlatIndex::remove_locked(int64_t n, const int64_t* del) {
+  std::vector<int64_t> rws;
+  L.remove_ids(n, del, rws);
+  if (!rws.empty()) {
+    long long* d_rows = scratch.alloc<long long>(rws.size());
+    B200VS_CUDA(cudaMemcpyAsync(d_rows, rws.data(), rws.size() * 8, cudaMemcpyHostToDevice, stream));
+    launch_set_ids(ids.p, d_rows, (int64_t)rws.size(), -1, stream);
+    B200VS_CUDA(cudaStreamSynchronize(stream));
+  }
+  return (int64_t)rws.size();
+}
+
+void IvfFlatIndex::maybe_compact() {
+  if (!L.needs_compaction()) return;
+  std::vector<long long> src, dst;
+  const int64_t new_rows = L.plan_compaction(src, dst);
+  DevBuf<float> nv; DevBuf<long long> ni; DevBuf<float> nn;
+  nv.reserve((size_t)std::max<int64_t>(new_rows, 1) * dim, 0, stream);
+  ni.reserve(std::max<int64_t>(new_rows, 1), 0, stream);
+  nn.reserve(std::max<int64_t>(new_rows, 1), 0, stream);
+  const int64_t m = (int64_t)src.size();
+  if (m) {
+    long long* d_src = scratch.alloc<long long>(m);
+    long long* d_dst = scratch.alloc<long long>(m);
+    B200VS_CUDA(cudaMemcpyAsync(d_src, src.data(), m * 8, cudaMemcpyHostToDevice, stream));
+    B200VS_CUDA(cudaMemcpyAsync(d_dst, dst.data(), m * 8, cudaMemcpyHostToDevice, stream));
+    launch_move_rows(vecs.p, ids.p, norms.p, d_src, d_dst, m, dim, nv.p, ni.p, nn.p, stream);
+  }
+  B200VS_CUDA(cudaStreamSynchronize(stream));
+  std::swap(vecs.p, nv.p); std::swap(vecs.cap, nv.cap);
+  std::swap(ids.p, ni.p); std::swap(ids.cap, ni.cap);
+  std::swap(norms.p, nn.p); std::swap(norms.cap, nn.cap);
+  L.commit_compaction();
+  L.upload(stream);
+  B200VS_CUDA(cudaStreamSynchronize(stream));
+}
+
+// VectorIndexIvfFlat::Delete, vector_index_ivf_flat.cc:162-189: untrained -> OK; nothing removed -> EVECTOR_INVALID.
+int64_t IvfFlatIndex::remove(int64_t n, const int64_t* del) {
+  std::unique_lock<std::shared_mutex> wl(rw);
+  if (!trained) return -1;  // signalled as OK by the ABI
+  std::lock_guard<std::mutex> gl(gpu_mu);
+  set_device();
+  scratch.reset(stream);
+  const int64_t r = remove_locked(n, del);
+  maybe_compact();
+  return r;
+}
+
+void fill_empty_results(int64_t nq, int k, float* od, long long* oi, cudaStream_t s) {
+  if (od) B200VS_CUDA(cudaMemsetAsync(od, 0, (size_t)nq * k * 4, s));
+  B200VS_CUDA(cudaMemsetAsync(oi, 0xFF, (size_t)nq * k * 8, s));  // -1
+}
+
+void IvfFlatIndex::search_dev(int64_t nq, const float* xq, int k, const SearchCtx& sc, float* od, long long* oi, cudaStream_t s) {
+  if (!trained) { fill_empty_results(nq, k, od, oi, s); return; }  // ivf_flat.cc:224-227
+  const float* q = prepare_queries(nq, xq, s);
+  const int nprobe = resolve_nprobe(sc);
+  long long* probes = coarse(nq, q, nprobe, s);
+  if (profiling) profile_probed(this, probes, nq * nprobe, nlist, L.d_len.p, s);
+  ScanJob j = list_job(sc, probes, nprobe);
+  j.dominant = true;
+  run_scan(this, j, nq, q, k, od, nullptr, oi, nullptr, s);
+}
+
+void IvfFlatIndex::range_search_dev(int64_t nq, const float* xq, float radius, int max_results, const SearchCtx& sc,
+                                    float* od, long long* oi, int* oc, cudaStream_t s) {
+  if (!trained) {
+    fill_empty_results(nq, max_results, od, oi, s);
+    if (oc) B200VS_CUDA(cudaMemsetAsync(oc, 0, (size_t)nq * 4, s));
+    return;
+  }
+  const float* q = prepare_queries(nq, xq, s);
+  const int nprobe = resolve_nprobe(sc);
+  long long* probes = coarse(nq, q, nprobe, s);
+  ScanJob j = list_job(sc, probes, nprobe);
+  j.has_thr = true;
+  j.thr_raw = ip_like() ? 1.0F - radius : radius;  // ivf_flat.cc:296-299
+  run_scan(this, j, nq, q, max_results, od, nullptr, oi, oc, s);
+}
+
+void IvfFlatIndex::export_lists(int64_t* list_off, float* vectors, uint8_t*, int64_t* out_ids) {
+  std::shared_lock<std::shared_mutex> rl(rw);
+  std::lock_guard<std::mutex> gl(gpu_mu);
+  set_device();
+  std::vector<float> rowbuf;
+  int64_t o = 0;
+  for (int l = 0; l < nlist; ++l) {
+    if (list_off) list_off[l] = o;
+    const auto& m = L.lists[l];
+    if (m.len == 0) continue;
+    if (vectors) {
+      rowbuf.resize((size_t)m.len * dim);
+      B200VS_CUDA(cudaMemcpy(rowbuf.data(), vecs.p + (size_t)m.off * dim, (size_t)m.len * dim * 4, cudaMemcpyDeviceToHost));
+    }
+    for (int p = 0; p < m.len; ++p) {
+      const int64_t id = L.h_ids[m.off + p];
+      if (id < 0) continue;
+      if (out_ids) out_ids[o] = id;
+      if (vectors) memcpy(vectors + (size_t)o * dim, rowbuf.data() + (size_t)p * dim, (size_t)dim * 4);
+      ++o;
+    }
+  }
+  if (list_off) list_off[nlist] = o;
+}
+
+IndexBase* make_ivf_flat(b200vs_metric m, int d, const b200vs_params& p) { return new IvfFlatIndex(m, d, p); }
+
+}  // namespace b200vs

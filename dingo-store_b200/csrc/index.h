@@ -1,0 +1,193 @@
+// index.h — host-side index objects of libb200vs (device memory owners + search orchestration).
+//
+// One object per dingo-store vector index (= per Raft region, src/vector/vector_index.h:54-55).  These are
+// the B200 replacements of the faiss / hnswlib objects the reference plugins own
+// (index_id_map2_ flat.cc:98, index_ ivf_flat.cc:809-816, raw_ivf_pq.cc:554-564, hnsw_index_ hnsw.cc:181).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/b200vs.h"
+#include "common.cuh"
+
+namespace b200vs {
+
+extern thread_local std::string g_last_error;
+struct StatusError {
+  int code;
+  std::string msg;
+};
+[[noreturn]] inline void fail(int code, const std::string& m) { throw StatusError{code, m}; }
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  void free() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  // grow to >= n elements; keeps the first `keep` elements (copied on `s`)
+  void reserve(size_t n, size_t keep, cudaStream_t s) {
+    if (n <= cap) return;
+    T* np = nullptr;
+    B200VS_CUDA(cudaMalloc(&np, n * sizeof(T)));
+    if (keep && p) B200VS_CUDA(cudaMemcpyAsync(np, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    if (p) { B200VS_CUDA(cudaStreamSynchronize(s)); cudaFree(p); }
+    p = np; cap = n;
+  }
+};
+
+// bump allocator for per-search scratch; reset at the start of every search (searches on one index are
+// serialised by gpu_mu and stream-ordered, so reuse is safe)
+struct Scratch {
+  DevBuf<unsigned char> buf;
+  size_t used = 0;
+  std::vector<std::pair<void*, size_t>> overflow;  // extra cudaMalloc blocks when buf is too small
+  ~Scratch() { release_overflow(); }
+  void release_overflow() { for (auto& o : overflow) cudaFree(o.first); overflow.clear(); }
+  void reset(cudaStream_t s) {
+    if (!overflow.empty()) {  // grow the main buffer so the next search fits without overflow blocks
+      size_t extra = 0;
+      for (auto& o : overflow) extra += o.second + 256;
+      B200VS_CUDA(cudaStreamSynchronize(s));
+      release_overflow();
+      size_t want = (buf.cap + extra) * 3 / 2;
+      buf.free();
+      buf.reserve(want, 0, s);
+    }
+    used = 0;
+  }
+  template <class T>
+  T* alloc(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) / 256 * 256;
+    if (used + bytes <= buf.cap) { T* r = reinterpret_cast<T*>(buf.p + used); used += bytes; return r; }
+    void* p = nullptr;
+    B200VS_CUDA(cudaMalloc(&p, bytes));
+    overflow.emplace_back(p, bytes);
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct SearchCtx {  // resolved per-search parameters, device filter included
+  int nprobe = 0;
+  int efsearch = 0;
+  int exact_only = 0;
+  int has_range = 0, negate = 0;
+  long long rmin = 0, rmax = 0;
+  const long long* sorted_ids_dev = nullptr;
+  long long n_ids = 0;
+  bool has_filter() const { return has_range || sorted_ids_dev; }
+};
+
+struct IndexBase {
+  b200vs_type type;
+  b200vs_metric metric;
+  int dim;
+  int device;
+  b200vs_params params;
+  cudaStream_t stream = nullptr;
+  cudaStream_t last_stream = nullptr;
+  std::shared_mutex rw;  // readers = searches, writers = add/remove/train (reference RWLock)
+  std::mutex gpu_mu;     // serialises scratch + stream use between concurrent readers
+  Scratch scratch;
+  int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool profiling = false;  // b200vs_set_profiling: time the dominant scan kernel with CUDA events
+
+  IndexBase(b200vs_type t, b200vs_metric m, int d, const b200vs_params& p);
+  virtual ~IndexBase();
+  void set_device() const { B200VS_CUDA(cudaSetDevice(device)); }
+  bool ip_like() const { return metric == B200VS_IP || metric == B200VS_COSINE; }
+
+  virtual void train(int64_t n, const float* x) { (void)n; (void)x; }
+  virtual bool is_trained() const { return true; }
+  virtual void set_state(const void* blob, size_t len) { (void)blob; (void)len; fail(B200VS_EVECTOR_NOT_SUPPORT, "no trained state for this index type"); }
+  virtual int64_t get_state(void* blob, size_t cap) { (void)blob; (void)cap; return 0; }
+  virtual void add(int64_t n, const float* x, const int64_t* ids, bool upsert) = 0;
+  virtual int64_t remove(int64_t n, const int64_t* ids) = 0;
+  // device-pointer search on stream s; scratch already reset; q is RAW (normalise inside for cosine)
+  virtual void search_dev(int64_t nq, const float* xq, int k, const SearchCtx& sc, float* out_dist, long long* out_ids,
+                          cudaStream_t s) = 0;
+  virtual void range_search_dev(int64_t nq, const float* xq, float radius, int max_results, const SearchCtx& sc,
+                                float* out_dist, long long* out_ids, int* out_counts, cudaStream_t s) {
+    (void)nq; (void)xq; (void)radius; (void)max_results; (void)sc; (void)out_dist; (void)out_ids; (void)out_counts; (void)s;
+    fail(B200VS_EVECTOR_NOT_SUPPORT, "range search not supported");
+  }
+  virtual int64_t count() const = 0;
+  virtual int64_t deleted_count() const { return 0; }
+  virtual int64_t memory_size() const = 0;
+  virtual void export_lists(int64_t* list_off, float* vectors, uint8_t* codes, int64_t* ids) = 0;
+  virtual void save(const std::string& path);
+  virtual void load(const std::string& path);
+
+  // helpers shared by the index types
+  const float* prepare_queries(int64_t nq, const float* xq_dev, cudaStream_t s);  // cosine -> normalised copy
+  void launch_count(int n = 1) { stats[0] += n; }
+};
+
+IndexBase* make_flat(b200vs_metric m, int d, const b200vs_params& p);
+IndexBase* make_ivf_flat(b200vs_metric m, int d, const b200vs_params& p);
+IndexBase* make_ivf_pq(b200vs_metric m, int d, const b200vs_params& p);
+IndexBase* make_hnsw(b200vs_metric m, int d, const b200vs_params& p);
+
+// ---- generic exact scan + select driver (scan_kernels.cuh) ----
+struct ScanJob {
+  bool l2 = true;
+  const float* vecs = nullptr;
+  const long long* ids = nullptr;
+  int d = 0;
+  int mode = 0;
+  long long n = 0;
+  const long long* probes = nullptr;
+  int nprobe = 0;
+  const long long* list_off = nullptr;
+  const int* list_len = nullptr;
+  double avg_candidates = 0;  // expected candidates per query (sizing of nsplit)
+  const SearchCtx* sc = nullptr;
+  bool has_thr = false;
+  float thr_raw = 0;  // range search: raw metric threshold (L2: dist < thr ; IP: ip > thr)
+  bool dominant = false;  // the list scan of an IVF search: timed when profiling is on
+};
+// profiling helpers: distinct probed lists / rows of a probe table
+void profile_probed(IndexBase* ix, const long long* probes, int64_t n_probes, int nlist, const int* list_len, cudaStream_t s);
+struct ScopedKernelTimer {  // CUDA events on the launching stream; synchronises in the destructor
+  IndexBase* ix; cudaStream_t s; cudaEvent_t e0 = nullptr, e1 = nullptr; bool on;
+  ScopedKernelTimer(IndexBase* ix_, cudaStream_t s_, bool on_) : ix(ix_), s(s_), on(on_) {
+    if (!on) return;
+    B200VS_CUDA(cudaEventCreate(&e0)); B200VS_CUDA(cudaEventCreate(&e1)); B200VS_CUDA(cudaEventRecord(e0, s));
+  }
+  void stop() {
+    if (!on || !e0) return;
+    cudaEventRecord(e1, s); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    ix->stats[3] += (int64_t)(ms * 1e6);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); e0 = e1 = nullptr;
+  }
+  ~ScopedKernelTimer() { stop(); }
+};
+// results: out_dist (API), out_raw (raw metric), out_ids, out_counts — any but out_ids may be null
+void run_scan(IndexBase* ix, const ScanJob& job, int64_t nq, const float* queries, int k, float* out_dist,
+              float* out_raw, long long* out_ids, int* out_counts, cudaStream_t s);
+
+void launch_normalize_faiss(float* x, int64_t n, int d, cudaStream_t s);
+void launch_normalize_hnsw(const float* x, float* out, int64_t n, int d, cudaStream_t s);
+void launch_scatter_rows(const float* src, const long long* src_ids, const long long* slots, int64_t n, int d,
+                         float* vecs, long long* ids, float* norms, cudaStream_t s);
+void launch_move_rows(const float* svecs, const long long* sids, const float* snorms, const long long* src_rows,
+                      const long long* dst_rows, int64_t n, int d, float* dvecs, long long* dids, float* dnorms,
+                      cudaStream_t s);
+void launch_set_ids(long long* ids, const long long* slots, int64_t n, long long value, cudaStream_t s);
+void launch_iota(long long* p, int64_t n, cudaStream_t s);
+void launch_merge_api(int nparts, int64_t nq, int k, const float* pd, const long long* pi, float* od, long long* oi,
+                      cudaStream_t s);
+
+}  // namespace b200vs

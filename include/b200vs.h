@@ -1,0 +1,148 @@
+/*
+ * b200vs.h — C ABI of the B200-native vector-search engine (libb200vs.so).
+ *
+ * This is the drop-in boundary behind dingo-store's C++ VectorIndex plugin surface
+ * (reference: src/vector/vector_index.h:56-279).  A thin C++ subclass of dingodb::VectorIndex
+ * (dingo-store_b200/host/vector_index_b200.{h,cc}; binding shown in INTEGRATION.md) marshals protobuf
+ * to flat arrays and calls these entry points; everything below the ABI is CUDA for sm_100a.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  No exception or abort crosses the ABI: every entry
+ *     point returns a b200vs_status; b200vs_last_error() gives a thread-local message.
+ *   - Status codes map 1:1 to the pb::error::Errno classes the reference plugins return
+ *     (src/vector/vector_index_flat.cc:209, :193-196; vector_index_ivf_flat.cc:112; vector_index_hnsw.cc:332-336,
+ *     :487-493; vector_index_utils.cc:551-561).
+ *   - Unless a function name ends in _device, all data pointers are HOST pointers.
+ *   - Distances are returned in the reference's API semantics (src/vector/vector_index_utils.cc:611-655):
+ *     L2 = squared L2; INNER_PRODUCT and COSINE = 1 - ip.  Results are ascending; rows with fewer than k
+ *     hits are padded with id = -1, dist = 0 (labels pre-filled -1, vector_index_flat.cc:218-219).
+ *   - Thread-safety: searches may be issued concurrently from many host threads (the reference calls
+ *     Search from a 16-thread pool, src/server/server.cc:868-873); writers are serialised against readers
+ *     by a reader/writer lock inside the index (reference: RWLock, src/common/synchronization.h:133-156).
+ */
+#ifndef B200VS_H_
+#define B200VS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200vs_index b200vs_index; /* opaque */
+
+/* replaces VectorIndexFactory::New type switch, src/vector/vector_index_factory.cc:40-95 */
+typedef enum { B200VS_FLAT = 0, B200VS_IVF_FLAT = 1, B200VS_IVF_PQ = 2, B200VS_HNSW = 3 } b200vs_type;
+/* mirrors pb::common::MetricType L2 / INNER_PRODUCT / COSINE */
+typedef enum { B200VS_L2 = 1, B200VS_IP = 2, B200VS_COSINE = 3 } b200vs_metric;
+
+typedef enum {
+  B200VS_OK = 0,
+  B200VS_EILLEGAL_PARAMETERS = 1, /* pb::error::EILLEGAL_PARAMTETERS */
+  B200VS_EVECTOR_INVALID = 2,     /* pb::error::EVECTOR_INVALID       */
+  B200VS_EVECTOR_NOT_TRAIN = 3,   /* pb::error::EVECTOR_NOT_TRAIN     */
+  B200VS_EVECTOR_NOT_SUPPORT = 4, /* pb::error::EVECTOR_NOT_SUPPORT   */
+  B200VS_EINTERNAL = 5,           /* pb::error::EINTERNAL             */
+  B200VS_EVECTOR_ID_DUPLICATED = 6 /* pb::error::EVECTOR_ID_DUPLICATED */
+} b200vs_status;
+
+/* creation parameters: the union of pb::common::Create{Flat,IvfFlat,IvfPq,Hnsw}Param fields read at
+ * vector_index_flat.cc:81-82, vector_index_ivf_flat.cc:75-83, vector_index_raw_ivf_pq.cc:60-75,
+ * vector_index_hnsw.cc:141-182.  0 = reference default (src/common/constant.h:177-188). */
+typedef struct {
+  int32_t nlist;        /* ncentroids; default 2048 */
+  int32_t pq_m;         /* nsubvector; default 64   */
+  int32_t pq_nbits;     /* nbits_per_idx; default 8 (only 8 is implemented) */
+  int32_t hnsw_m;       /* nlinks */
+  int32_t hnsw_efc;     /* efconstruction */
+  int64_t max_elements; /* hnsw max_elements */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t reserved;
+} b200vs_params;
+
+/* search-time parameters: pb::common::VectorSearchParameter knobs (ivf_flat().nprobe() ivf_flat.cc:211,
+ * ivf_pq().nprobe() raw_ivf_pq.cc:170, hnsw().efsearch() hnsw.cc:332) plus the device form of the
+ * reference's FilterFunctors (vector_index.h:67-146): all given filters are ANDed. */
+typedef struct {
+  int32_t nprobe;   /* <=0 -> 80 (Constant::kSearchIvfFlatParamNprobe); clamped to nlist */
+  int32_t efsearch; /* 0 -> keep the sticky ef; outside [0,1024] -> EILLEGAL_PARAMETERS */
+  int32_t has_range; /* RangeFilterFunctor: range_min <= id < range_max */
+  int32_t negate;    /* SortFilterFunctor / ConcreteFilterFunctor is_negation */
+  int64_t range_min, range_max;
+  const int64_t* sorted_ids; /* ascending id list (HOST pointer), or NULL */
+  int64_t n_ids;
+  int32_t exact_only; /* 1 = force the exact FP32 scan (skip the tensor-core candidate pass) */
+  int32_t reserved;
+} b200vs_search_params;
+
+/* lifecycle — replaces the plugin constructors / destructors */
+int b200vs_create(b200vs_type type, b200vs_metric metric, int32_t dim, const b200vs_params* params, b200vs_index** out);
+void b200vs_destroy(b200vs_index* idx);
+
+/* VectorIndex::Train(std::vector<float>&) — vector_index_ivf_flat.cc:644-712, raw_ivf_pq.cc:457-500,
+ * ivf_pq.cc:327-395.  x row-major [n,dim], RAW values (COSINE is normalised inside).  Flat/HNSW: no-op. */
+int b200vs_train(b200vs_index* idx, int64_t n, const float* x);
+/* Load / fetch trained state (IVF centroids, PQ codebooks, HNSW graph) as a flat blob — used to search the
+ * SAME trained index as the CPU path.  Layouts: see DESIGN.md §Trained-state blobs. */
+int b200vs_set_trained_state(b200vs_index* idx, const void* blob, size_t len);
+int64_t b200vs_get_trained_state(b200vs_index* idx, void* blob, size_t cap); /* returns bytes needed/written, <0 on error */
+
+/* VectorIndex::Add / Upsert / Delete — flat.cc:121-203, ivf_flat.cc:92-190, hnsw.cc:203-281.
+ * ids must be unique within one call (EVECTOR_ID_DUPLICATED); upsert=1 removes pre-existing ids first. */
+int b200vs_add_with_ids(b200vs_index* idx, int64_t n, const float* x, const int64_t* ids, int upsert);
+int b200vs_remove_ids(b200vs_index* idx, int64_t n, const int64_t* ids, int64_t* n_removed);
+
+/* VectorIndex::Search — flat.cc:205-264, ivf_flat.cc:191-275, raw_ivf_pq.cc:157-210, hnsw.cc:318-485.
+ * xq row-major [nq,dim] RAW; out_dist [nq,k], out_ids [nq,k]. */
+int b200vs_search(b200vs_index* idx, int64_t nq, const float* xq, int32_t k, const b200vs_search_params* sp,
+                  float* out_dist, int64_t* out_ids);
+/* Same, with xq / out_dist / out_ids DEVICE pointers on the index's device; enqueued on `stream`
+ * (a cudaStream_t, NULL = the index's own stream) and NOT synchronised when it returns. */
+int b200vs_search_device(b200vs_index* idx, int64_t nq, const float* xq_dev, int32_t k,
+                         const b200vs_search_params* sp, float* out_dist_dev, int64_t* out_ids_dev, void* stream);
+
+/* VectorIndex::RangeSearch — flat.cc:267-323, ivf_flat.cc:278-368 (HNSW: EVECTOR_NOT_SUPPORT, hnsw.cc:487-493).
+ * radius in API semantics (mapped 1-r for IP/COSINE, flat.cc:282-285).  At most max_results hits per
+ * query are kept (closest first); out_counts[nq] receives the per-query hit count. */
+int b200vs_range_search(b200vs_index* idx, int64_t nq, const float* xq, float radius, int32_t max_results,
+                        const b200vs_search_params* sp, float* out_dist, int64_t* out_ids, int32_t* out_counts);
+
+/* GetCount / GetDeletedCount / GetMemorySize / IsTrained / NeedTrain — vector_index.h:150-152,:199-200 */
+int b200vs_count(b200vs_index* idx, int64_t* count);
+int b200vs_deleted_count(b200vs_index* idx, int64_t* count);
+int b200vs_memory_size(b200vs_index* idx, int64_t* bytes);
+int b200vs_is_trained(b200vs_index* idx);
+int32_t b200vs_dimension(b200vs_index* idx);
+
+/* Save / Load — vector_index.h:168-170 (own container format; faiss/hnswlib file
+ * compatibility is SURVEY §8(f)-4, not built). */
+int b200vs_save(b200vs_index* idx, const char* path);
+int b200vs_load(b200vs_index* idx, const char* path);
+
+/* Export the inverted lists in list-major order (list l owns rows [list_off[l], list_off[l+1])) so a CPU
+ * implementation can search the identical index.  Any output pointer may be NULL.  Flat: nlist = 1. */
+int b200vs_export_lists(b200vs_index* idx, int64_t* list_off /*[nlist+1]*/, float* vectors /*[count,dim]*/,
+                        uint8_t* codes /*[count,pq_m]*/, int64_t* ids /*[count]*/);
+
+/* k-way merge of per-shard top-k, the engine's analogue of VectorIndexWrapper::MergeSearchResults
+ * (src/vector/vector_index.cc:1056-1108).  parts_* are DEVICE arrays [nparts, nq, k] (API-semantics
+ * distances ascending, id -1 padded) e.g. the output of one ncclAllGather; out_* DEVICE [nq,k]. */
+int b200vs_merge_topk_device(int32_t device, int32_t nparts, int64_t nq, int32_t k, const float* parts_dist,
+                             const int64_t* parts_ids, float* out_dist, int64_t* out_ids, void* stream);
+
+/* Counters of the last search on this index: [0] kernels launched, [1] queries served by the tensor-core
+ * candidate pass, [2] queries that failed certification and were re-run on the exact path; with profiling on
+ * (b200vs_set_profiling) also [3] device time of the dominant list-scan kernel in ns (CUDA events on the launch
+ * stream), [4] rows in the distinct probed lists, [5] distinct probed lists.  Profiling synchronises the stream
+ * inside the call: never leave it on in a timed run. */
+int b200vs_last_search_stats(b200vs_index* idx, int64_t stats[8]);
+int b200vs_set_profiling(b200vs_index* idx, int on);
+
+const char* b200vs_last_error(void);
+const char* b200vs_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VS_H_ */

@@ -1,0 +1,166 @@
+"""Behavioural checks of the oracle's search restatements (the reference's unit tests assert contracts, not
+numbers: SURVEY.md §4) plus cross-checks against float64 numpy brute force."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from oracle_lib import COSINE, IP, L2
+
+
+def brute(metric, xb, xq, k):
+    xb64, xq64 = xb.astype(np.float64), xq.astype(np.float64)
+    if metric == L2:
+        d = ((xq64[:, None, :] - xb64[None, :, :]) ** 2).sum(-1)
+    else:
+        d = -(xq64 @ xb64.T)
+    return np.argsort(d, axis=1, kind="stable")[:, :k]
+
+
+@pytest.mark.parametrize("metric", [L2, IP, COSINE])
+def test_flat_matches_float64_bruteforce(oracle, metric):
+    rng = np.random.default_rng(3)
+    xb = rng.random((500, 24)).astype(np.float32)
+    xq = rng.random((7, 24)).astype(np.float32)
+    ids = np.arange(1000, 1500, dtype=np.int64)
+    stored = oracle.normalize_faiss(xb) if metric == COSINE else xb
+    D, I = oracle.flat_search(metric, stored, ids, xq, 10)
+    qn = oracle.normalize_faiss(xq) if metric == COSINE else xq
+    want = ids[brute(L2 if metric == L2 else IP, stored, qn, 10)]
+    assert (I == want).mean() > 0.98  # float32 vs float64 may swap near-ties
+    assert np.all(np.diff(D, axis=1) >= 0)  # ascending in API semantics
+    if metric != L2:  # 1 - ip
+        ip = (qn.astype(np.float64) @ stored.astype(np.float64).T)
+        assert np.allclose(D[:, 0], 1 - ip.max(1), atol=1e-5)
+
+
+def test_flat_reference_fixture_contract(oracle):
+    # reference Flat fixture: 10 x 8 (test_vector_index_flat.cc:44-47,:491-500); self query -> itself at rank 0
+    xb = oracle.fixture(10, 8)
+    ids = np.arange(1, 11, dtype=np.int64)
+    D, I = oracle.flat_search(L2, xb, ids, xb[:3], 3)
+    assert list(I[:, 0]) == [1, 2, 3] and np.all(D[:, 0] == 0)
+    # fewer vectors than k -> padded with -1 (labels pre-filled -1, flat.cc:218-219)
+    D, I = oracle.flat_search(L2, xb, ids, xb[:1], 20)
+    assert (I[0, 10:] == -1).all() and (I[0, :10] >= 1).all()
+
+
+def test_flat_filters_and_removed_slots(oracle):
+    rng = np.random.default_rng(4)
+    xb = rng.random((200, 16)).astype(np.float32)
+    ids = np.arange(1, 201, dtype=np.int64)
+    ids[10:20] = -1  # removed
+    xq = rng.random((4, 16)).astype(np.float32)
+    D, I = oracle.flat_search(L2, xb, ids, xq, 50, id_range=(50, 100))
+    assert ((I >= 50) & (I < 100)).all()
+    allow = np.array([3, 5, 77, 150], np.int64)
+    D, I = oracle.flat_search(L2, xb, ids, xq, 10, sorted_ids=allow)
+    assert set(I[0][I[0] >= 0]) == set(allow)
+    D, I = oracle.flat_search(L2, xb, ids, xq, 200, sorted_ids=allow, negate=True)
+    got = set(I[0][I[0] >= 0])
+    assert not (got & set(allow)) and not (got & set(range(11, 21))) and len(got) == 200 - 10 - 4
+
+
+def test_ties_break_by_id(oracle):
+    xb = np.ones((6, 4), np.float32)
+    ids = np.array([9, 3, 7, 1, 5, 2], np.int64)
+    D, I = oracle.flat_search(L2, xb, ids, np.zeros((1, 4), np.float32), 4)
+    assert list(I[0]) == [1, 2, 3, 5]
+
+
+def make_ivf(oracle, metric, n=3000, d=16, nlist=20, seed=5):
+    rng = np.random.default_rng(seed)
+    xb = rng.random((n, d)).astype(np.float32)
+    stored = oracle.normalize_faiss(xb) if metric == COSINE else xb
+    cent = oracle.kmeans(metric, stored, nlist)
+    asg = oracle.assign(metric, stored, cent)
+    order = np.argsort(asg, kind="stable")
+    off = np.zeros(nlist + 1, np.int64)
+    off[1:] = np.cumsum(np.bincount(asg, minlength=nlist))
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    return xb, stored, cent, off, stored[order], ids[order], ids
+
+
+@pytest.mark.parametrize("metric", [L2, IP, COSINE])
+def test_ivfflat_full_probe_equals_flat(oracle, metric):
+    xb, stored, cent, off, lx, lids, ids = make_ivf(oracle, metric)
+    xq = np.random.default_rng(6).random((9, 16)).astype(np.float32)
+    Df, If = oracle.flat_search(metric, stored, ids, xq, 10)
+    Di, Ii = oracle.ivfflat_search(metric, cent, off, lx, lids, xq, 10, nprobe=20)
+    assert np.array_equal(If, Ii) and np.array_equal(Df, Di)
+    # nprobe is clamped to nlist (ivf_flat.cc:234); <= 0 means the default 80 (constant.h:178)
+    Dc, Ic = oracle.ivfflat_search(metric, cent, off, lx, lids, xq, 10, nprobe=500)
+    Dd, Id = oracle.ivfflat_search(metric, cent, off, lx, lids, xq, 10, nprobe=0)
+    assert np.array_equal(Ic, If) and np.array_equal(Id, If)
+
+
+def test_ivfflat_partial_probe_recall_and_subset(oracle):
+    xb, stored, cent, off, lx, lids, ids = make_ivf(oracle, L2)
+    xq = np.random.default_rng(7).random((20, 16)).astype(np.float32)
+    Df, If = oracle.flat_search(L2, stored, ids, xq, 10)
+    Di, Ii = oracle.ivfflat_search(L2, cent, off, lx, lids, xq, 10, nprobe=5)
+    recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(If, Ii)])
+    assert recall > 0.6
+    assert np.all(np.diff(Di, axis=1) >= 0)
+
+
+def test_kmeans_is_deterministic_and_reasonable(oracle):
+    rng = np.random.default_rng(8)
+    centers = rng.random((8, 6)).astype(np.float32) * 10
+    x = (centers[rng.integers(0, 8, 4000)] + rng.standard_normal((4000, 6)) * 0.1).astype(np.float32)
+    c1 = oracle.kmeans(L2, x, 8, nthreads=1)
+    c2 = oracle.kmeans(L2, x, 8, nthreads=4)
+    assert np.array_equal(c1, c2)
+    asg = oracle.assign(L2, x, c1)
+    err = ((x - c1[asg]) ** 2).sum(1).mean()
+    assert err < 0.3 * x.var(0).sum()  # Lloyd from random points: a local optimum, far below the data variance
+
+
+def test_ivfpq_search_sanity(oracle):
+    rng = np.random.default_rng(9)
+    n, d, nlist, M = 6000, 32, 16, 8
+    xb = rng.standard_normal((n, d)).astype(np.float32)
+    for metric in (L2, IP):
+        cent = oracle.kmeans(metric, xb, nlist)
+        asg = oracle.assign(metric, xb, cent)
+        cb = oracle.pq_train(xb - cent[asg], M)
+        codes = oracle.ivfpq_encode(cb, cent, xb, asg)
+        order = np.argsort(asg, kind="stable")
+        off = np.zeros(nlist + 1, np.int64)
+        off[1:] = np.cumsum(np.bincount(asg, minlength=nlist))
+        ids = np.arange(n, dtype=np.int64)
+        xq = xb[:50] + 0.01 * rng.standard_normal((50, d)).astype(np.float32)
+        D, I = oracle.ivfpq_search(metric, cent, cb, off, codes[order], ids[order], xq, 10, nprobe=nlist)
+        Df, If = oracle.flat_search(metric, xb, ids, xq, 10)
+        recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(If, I)])
+        assert recall > 0.35, (metric, recall)
+        assert np.all(np.diff(D, axis=1) >= 0)
+        # distances approximate the true ones (PQ reconstruction error only)
+        recon = cent[asg] + np.stack([cb[m, codes[:, m]] for m in range(M)], 1).reshape(n, d)
+        j = I[0, 0]
+        true = ((xq[0] - recon[j]) ** 2).sum() if metric == L2 else 1 - xq[0] @ recon[j]
+        assert abs(D[0, 0] - true) < 1e-3 * max(1, abs(true))
+
+
+@pytest.mark.parametrize("metric", [L2, IP, COSINE])
+def test_hnsw_recall_and_contract(oracle, metric):
+    rng = np.random.default_rng(10)
+    n, d = 2000, 16
+    xb = rng.random((n, d)).astype(np.float32)
+    labels = np.arange(100, 100 + n, dtype=np.int64)
+    h = oracle_lib.OracleHnsw(oracle, metric, d, n, 16, 200)
+    h.add(xb, labels)
+    xq = rng.random((30, d)).astype(np.float32)
+    D, I, nd, nh = h.search(xq, 10, ef=128)
+    assert (I >= 100).all() and np.all(np.diff(D, axis=1) >= 0)  # exactly k hits, ascending (hnsw.cc:400-419)
+    stored = oracle.normalize_hnsw(xb) if metric == COSINE else xb
+    qn = oracle.normalize_hnsw(xq) if metric == COSINE else xq
+    want = labels[brute(L2 if metric == L2 else IP, stored, qn, 10)]
+    recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(want, I)])
+    assert recall > 0.9, recall
+    assert (nd > 0).all() and (nh > 0).all()
+    # filter: traversed but never returned
+    D2, I2, _, _ = h.search(xq, 10, ef=128, id_range=(100, 600))
+    assert ((I2 >= 100) & (I2 < 600) | (I2 == -1)).all()
+    blob = h.export()
+    hdr = blob[:64].view(np.int64)
+    assert hdr[0] == 0x57534E48 and hdr[1] == n and hdr[2] == d
