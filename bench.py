@@ -251,7 +251,8 @@ def main():
     out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
     sp, _keep = b200vs.make_search_params(nprobe=args.nprobe, exact_only=args.exact_only)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream: the library launches on it and the events time it
+    torch.cuda.set_stream(stream)
     if world > 1:
         g_d = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
         g_i = torch.empty((world, nq, k), dtype=torch.int64, device=dev)

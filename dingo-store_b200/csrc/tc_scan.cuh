@@ -1,0 +1,84 @@
+// tc_scan.cuh — tensor-core candidate pass for Flat / IVF-Flat search (sm_100a: TMA + tcgen05 + TMEM).
+//
+// What it replaces: the per-query CPU scans IVFFlatScanner::scan_codes / exhaustive_*_seq behind
+// VectorIndexIvfFlat::Search and VectorIndexFlat::Search (src/vector/vector_index_ivf_flat.cc:247-251,
+// vector_index_flat.cc:249-252).  The reference streams every probed list once PER QUERY on one core; here
+// each probed list (chunk) is streamed from HBM ONCE PER BATCH and multiplied against all queries that probe
+// it — the one place on this path where the work is a dense contraction.
+//
+// Exactness: the MMA runs in TF32 (operands truncated to 10 mantissa bits), so its scores only SELECT
+// candidates.  Per query the engine keeps every row whose approximate score is within 2*eps of the k-th best
+// approximate score (eps = rigorous bound on the TF32 score error); all of those are re-scored by the exact
+// FP32 kernel in the reference's AVX-512 order, so the returned ids and distances are identical to the exact
+// path.  Queries whose window cannot be certified (candidate overflow / threshold too tight) are re-run on
+// the exact scan.  See DESIGN.md §Tensor-core candidate pass.
+#pragma once
+#include <cuda.h>
+
+#include "index.h"
+#include "scan_kernels.cuh"
+
+namespace b200vs {
+
+constexpr int TC_BM = 128;       // database rows per MMA tile (UMMA M)
+constexpr int TC_BK = 32;        // floats per K block = 128 B = one swizzle span
+constexpr int TC_NQT = 64;       // queries per work item (UMMA N <= 64)
+constexpr int TC_STAGES = 6;     // TMA->MMA ring depth
+constexpr int TC_THREADS = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
+constexpr int TC_CHUNK = 2048;   // rows per work item (list chunk)
+constexpr int TC_SAMPLE = 32;    // sampled rows per chunk for the threshold estimate
+constexpr uint32_t TC_A_BYTES = TC_BM * 128;
+constexpr uint32_t TC_B_BYTES = TC_NQT * 128;
+constexpr size_t TC_SMEM = (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024;
+
+struct TcItem {
+  int list;
+  int row_begin, row_end;  // rows within the list
+  int pair_begin;          // first row of this item's query group in the gathered-query workspace
+  int nq;                  // queries in the group (1..TC_NQT)
+  int pad[3];
+};
+
+struct TcParams {
+  const long long* ids;
+  const float* norms;
+  const long long* list_off;
+  int d;
+  const TcItem* items;
+  const int* n_items;
+  const int* pair_query;  // [npairs] query index of each gathered row
+  int mode;               // 0 = sample pass (dense scores of the first TC_SAMPLE rows), 1 = full pass
+  float* sample;          // [items, TC_NQT, TC_SAMPLE]
+  const float* tau;       // [nq] capture threshold on the approximate score
+  unsigned long long* cand;  // [nq, cap]  (ord(score) << 32 | arena row)
+  int* cand_cnt;             // [nq]
+  int cap;
+  int l2;
+  FilterDev filt;
+};
+
+// view of an index the tile scan can run on (lists contiguous in one arena)
+struct TcView {
+  const float* vecs = nullptr;
+  const long long* ids = nullptr;
+  const float* norms = nullptr;
+  int64_t arena_rows = 0;       // rows addressable by the A tensor map
+  const long long* list_off = nullptr;  // device [nlist]
+  const int* list_len = nullptr;        // device [nlist]
+  int nlist = 0;
+  int64_t total_chunks = 0;     // sum over lists of ceil(len / TC_CHUNK)   (host bookkeeping)
+  int max_chunks_per_list = 0;
+  float max_norm = 0.f;         // max ||x|| over the index (host bookkeeping, monotone)
+};
+
+// true when this search can use the tensor-core pass (otherwise the caller runs the exact scan)
+bool tc_eligible(const IndexBase* ix, const TcView& v, int64_t nq, int k, int nprobe, const SearchCtx& sc);
+
+// probes: device [nq, nprobe] list indices (for Flat: all zeros, nprobe = 1).  q: device queries, already
+// normalised for cosine.  Writes API-semantics results.  Falls back per query to the exact scan via `exact`.
+void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float* q, int k, const long long* probes,
+               int nprobe, const SearchCtx& sc, float* out_dist, long long* out_ids, cudaStream_t s);
+
+float device_max_norm(IndexBase* ix, const float* norms_sq, int64_t n, cudaStream_t s);  // sqrt(max ||x||^2)
+
+}  // namespace b200vs
