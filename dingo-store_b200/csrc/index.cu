@@ -7,6 +7,7 @@
 
 #include "index.h"
 #include "ivf_common.h"
+#include "tc_scan.cuh"
 
 namespace b200vs {
 
@@ -57,8 +58,27 @@ struct FlatIndex : IndexBase {
   std::vector<int64_t> h_ids;
   std::unordered_map<int64_t, int64_t> id2row;
   int64_t ndeleted = 0;
+  DevBuf<long long> d_off1;  // the single "list" of a Flat index, for the tile-scan view
+  DevBuf<int> d_len1;
+  float max_norm = 0.f;
 
-  FlatIndex(b200vs_metric m, int d, const b200vs_params& p) : IndexBase(B200VS_FLAT, m, d, p) {}
+  FlatIndex(b200vs_metric m, int d, const b200vs_params& p) : IndexBase(B200VS_FLAT, m, d, p) {
+    d_off1.reserve(1, 0, stream); d_len1.reserve(1, 0, stream);
+    B200VS_CUDA(cudaMemsetAsync(d_off1.p, 0, 8, stream));
+    B200VS_CUDA(cudaMemsetAsync(d_len1.p, 0, 4, stream));
+    B200VS_CUDA(cudaStreamSynchronize(stream));
+  }
+  void publish_len() {
+    const int len = (int)std::min<int64_t>(rows, 0x7fffffff);
+    B200VS_CUDA(cudaMemcpyAsync(d_len1.p, &len, 4, cudaMemcpyHostToDevice, stream));
+    B200VS_CUDA(cudaStreamSynchronize(stream));
+  }
+  TcView view() const {
+    TcView v;
+    v.vecs = vecs.p; v.ids = ids.p; v.norms = norms.p; v.arena_rows = rows; v.list_off = d_off1.p; v.list_len = d_len1.p;
+    v.nlist = 1; v.flat = true; v.total_chunks = (rows + TC_CHUNK - 1) / TC_CHUNK; v.max_chunks_per_list = (int)v.total_chunks; v.max_norm = max_norm;
+    return v;
+  }
 
   void reserve_rows(int64_t need) {
     if ((size_t)need * dim <= vecs.cap) return;
@@ -105,6 +125,7 @@ struct FlatIndex : IndexBase {
     for (int64_t i = 0; i < live; ++i) { nh[i] = h_ids[src[i]]; id2row[nh[i]] = i; }
     h_ids.swap(nh);
     rows = live; ndeleted = 0;
+    publish_len();
   }
 
   // VectorIndexFlat::AddOrUpsert, vector_index_flat.cc:121-162: duplicate ids inside the batch are rejected,
@@ -131,11 +152,14 @@ struct FlatIndex : IndexBase {
     B200VS_CUDA(cudaMemcpyAsync(st_ids, in_ids, (size_t)n * 8, cudaMemcpyHostToDevice, stream));
     B200VS_CUDA(cudaMemcpyAsync(st_slots, slots.data(), (size_t)n * 8, cudaMemcpyHostToDevice, stream));
     if (metric == B200VS_COSINE) launch_normalize_faiss(st, n, dim, stream);  // flat.cc:155 (normalize_)
-    launch_scatter_rows(st, st_ids, st_slots, n, dim, vecs.p, ids.p, norms.p, stream);
+    float* st_norms = scratch.alloc<float>(n);
+    launch_scatter_rows(st, st_ids, st_slots, n, dim, vecs.p, ids.p, norms.p, st_norms, stream);
+    max_norm = std::max(max_norm, device_max_norm(this, st_norms, n, stream));
     B200VS_CUDA(cudaStreamSynchronize(stream));
     h_ids.resize(rows + n);
     for (int64_t i = 0; i < n; ++i) { h_ids[rows + i] = in_ids[i]; id2row[in_ids[i]] = rows + i; }
     rows += n;
+    publish_len();
     compact_if_needed();
   }
 
@@ -165,6 +189,13 @@ struct FlatIndex : IndexBase {
 
   void search_dev(int64_t nq, const float* xq, int k, const SearchCtx& sc, float* od, long long* oi, cudaStream_t s) override {
     const float* q = prepare_queries(nq, xq, s);
+    const TcView v = view();
+    if (rows > 0 && tc_eligible(this, v, nq, k, 1, sc)) {
+      long long* probes = scratch.alloc<long long>(nq);
+      B200VS_CUDA(cudaMemsetAsync(probes, 0, (size_t)nq * 8, s));
+      tc_search(this, v, metric == B200VS_L2, nq, q, k, probes, 1, sc, od, oi, s);
+      return;
+    }
     run_scan(this, job(sc), nq, q, k, od, nullptr, oi, nullptr, s);
   }
 
@@ -221,6 +252,13 @@ struct IvfFlatIndex : IndexBase {
   DevBuf<long long> ids;         // arena
   DevBuf<float> norms;           // arena
   IvfLists L;                    // host bookkeeping + device list_off/list_len
+  float max_norm = 0.f;
+  TcView view() const {
+    TcView v;
+    v.vecs = vecs.p; v.ids = ids.p; v.norms = norms.p; v.arena_rows = L.arena_used; v.list_off = L.d_off.p; v.list_len = L.d_len.p;
+    v.nlist = nlist; v.total_chunks = L.total_chunks; v.max_chunks_per_list = L.max_chunks_per_list; v.max_norm = max_norm;
+    return v;
+  }
 
   IvfFlatIndex(b200vs_metric m, int d, const b200vs_params& p) : IndexBase(B200VS_IVF_FLAT, m, d, p) {
     nlist = p.nlist > 0 ? p.nlist : 2048;  // Constant::kCreateIvfFlatParamNcentroids
@@ -380,7 +418,9 @@ void IvfFlatIndex::add(int64_t n, const float* x, const int64_t* in_ids, bool up
   });
   for (int64_t i = 0; i < n; ++i) slots[i] = L.append((int)h_list[i], in_ids[i]);
   B200VS_CUDA(cudaMemcpyAsync(st_slots, slots.data(), (size_t)n * 8, cudaMemcpyHostToDevice, stream));
-  launch_scatter_rows(st, st_ids, st_slots, n, dim, vecs.p, ids.p, norms.p, stream);
+  float* st_norms = scratch.alloc<float>(n);
+  launch_scatter_rows(st, st_ids, st_slots, n, dim, vecs.p, ids.p, norms.p, st_norms, stream);
+  max_norm = std::max(max_norm, device_max_norm(this, st_norms, n, stream));
   L.upload(stream);
   B200VS_CUDA(cudaStreamSynchronize(stream));
 }
@@ -445,6 +485,11 @@ void IvfFlatIndex::search_dev(int64_t nq, const float* xq, int k, const SearchCt
   const int nprobe = resolve_nprobe(sc);
   long long* probes = coarse(nq, q, nprobe, s);
   if (profiling) profile_probed(this, probes, nq * nprobe, nlist, L.d_len.p, s);
+  const TcView v = view();
+  if (L.live > 0 && tc_eligible(this, v, nq, k, nprobe, sc)) {
+    tc_search(this, v, metric == B200VS_L2, nq, q, k, probes, nprobe, sc, od, oi, s);
+    return;
+  }
   ScanJob j = list_job(sc, probes, nprobe);
   j.dominant = true;
   run_scan(this, j, nq, q, k, od, nullptr, oi, nullptr, s);

@@ -181,7 +181,7 @@ void run_scan(IndexBase* ix, const ScanJob& job, int64_t nq, const float* querie
 void launch_normalize_faiss(float* x, int64_t n, int d, cudaStream_t s);
 void launch_normalize_hnsw(const float* x, float* out, int64_t n, int d, cudaStream_t s);
 void launch_scatter_rows(const float* src, const long long* src_ids, const long long* slots, int64_t n, int d,
-                         float* vecs, long long* ids, float* norms, cudaStream_t s);
+                         float* vecs, long long* ids, float* norms, float* row_norms, cudaStream_t s);
 void launch_move_rows(const float* svecs, const long long* sids, const float* snorms, const long long* src_rows,
                       const long long* dst_rows, int64_t n, int d, float* dvecs, long long* dids, float* dnorms,
                       cudaStream_t s);

@@ -16,8 +16,24 @@ static void ensure_smem(K kernel, size_t bytes) {
   B200VS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
 }
 
+static void run_scan_impl(IndexBase* ix, const ScanJob& job, int64_t nq, const float* queries, int k, float* out_dist,
+                          float* out_raw, long long* out_ids, int* out_counts, const int* qmap, const int* qcount,
+                          int forced_nsplit, cudaStream_t s);
+
 void run_scan(IndexBase* ix, const ScanJob& job, int64_t nq, const float* queries, int k, float* out_dist,
               float* out_raw, long long* out_ids, int* out_counts, cudaStream_t s) {
+  run_scan_impl(ix, job, nq, queries, k, out_dist, out_raw, out_ids, out_counts, nullptr, nullptr, 0, s);
+}
+
+// exact re-run of the queries listed in qmap[0 .. *qcount) (device-side count; grid sized for nq_max)
+void run_scan_mapped(IndexBase* ix, const ScanJob& job, int64_t nq_max, const int* qmap, const int* qcount, const float* queries,
+                     int k, float* out_dist, long long* out_ids, cudaStream_t s) {
+  run_scan_impl(ix, job, nq_max, queries, k, out_dist, nullptr, out_ids, nullptr, qmap, qcount, 8, s);
+}
+
+static void run_scan_impl(IndexBase* ix, const ScanJob& job, int64_t nq, const float* queries, int k, float* out_dist,
+                          float* out_raw, long long* out_ids, int* out_counts, const int* qmap, const int* qcount,
+                          int forced_nsplit, cudaStream_t s) {
   if (nq <= 0 || k <= 0) return;
   if (nq > 65535) fail(B200VS_EILLEGAL_PARAMETERS, "batch too large (max 65535 queries per call)");
   // split each query's candidate range over several CTAs when the batch alone cannot fill 148 SMs
@@ -26,6 +42,7 @@ void run_scan(IndexBase* ix, const ScanJob& job, int64_t nq, const float* querie
   const double cand = job.mode == 0 ? (double)job.n : job.avg_candidates;
   const int max_by_work = (int)std::max(1.0, cand / 512.0);
   nsplit = std::max(1, std::min(nsplit, std::min(max_by_work, 128)));
+  if (forced_nsplit > 0) nsplit = forced_nsplit;
 
   const int cap = select_pool_cap(k, SCAN_THREADS);  // SCAN_THREADS >= SCAN_QUADS: one size for both kernels
   ScanArgs a;
@@ -43,6 +60,7 @@ void run_scan(IndexBase* ix, const ScanJob& job, int64_t nq, const float* querie
   a.has_thr = job.has_thr ? 1 : 0;
   a.thr_key = job.has_thr ? f2ord(job.l2 ? job.thr_raw : -job.thr_raw) : 0;
   a.pool_cap = cap;
+  a.qmap = qmap; a.qcount = qcount;
 
   const size_t smem1 = scan_smem_bytes(job.d, job.mode == 0 ? 1 : job.nprobe, cap);
   const size_t smem2 = BlockSelect::smem_bytes(cap);
@@ -53,13 +71,13 @@ void run_scan(IndexBase* ix, const ScanJob& job, int64_t nq, const float* querie
     scan_select_kernel<true><<<grid, SCAN_THREADS, smem1, s>>>(a);
     timer.stop();
     ensure_smem(merge_select_kernel<true>, smem2);
-    merge_select_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, nsplit, k, cap, out_dist, out_raw, out_ids, out_counts);
+    merge_select_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, nsplit, k, cap, out_dist, out_raw, out_ids, out_counts, qmap, qcount);
   } else {
     ensure_smem(scan_select_kernel<false>, smem1);
     scan_select_kernel<false><<<grid, SCAN_THREADS, smem1, s>>>(a);
     timer.stop();
     ensure_smem(merge_select_kernel<false>, smem2);
-    merge_select_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, nsplit, k, cap, out_dist, out_raw, out_ids, out_counts);
+    merge_select_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, nsplit, k, cap, out_dist, out_raw, out_ids, out_counts, qmap, qcount);
   }
   B200VS_CUDA(cudaGetLastError());
   ix->launch_count(2);
@@ -100,10 +118,10 @@ void launch_normalize_hnsw(const float* x, float* out, int64_t n, int d, cudaStr
   B200VS_CUDA(cudaGetLastError());
 }
 void launch_scatter_rows(const float* src, const long long* src_ids, const long long* slots, int64_t n, int d,
-                         float* vecs, long long* ids, float* norms, cudaStream_t s) {
+                         float* vecs, long long* ids, float* norms, float* row_norms, cudaStream_t s) {
   if (n <= 0) return;
   const int threads = 256;
-  scatter_rows_kernel<<<(unsigned)cdiv(n * 4, threads), threads, 0, s>>>(src, src_ids, slots, n, d, vecs, ids, norms);
+  scatter_rows_kernel<<<(unsigned)cdiv(n * 4, threads), threads, 0, s>>>(src, src_ids, slots, n, d, vecs, ids, norms, row_norms);
   B200VS_CUDA(cudaGetLastError());
 }
 void launch_move_rows(const float* svecs, const long long* sids, const float* snorms, const long long* src_rows,

@@ -8,34 +8,10 @@
 // They are also the rerank stage of the tensor-core candidate pass (tc_ivf.cuh) and its fallback.
 #pragma once
 #include "common.cuh"
+#include "filter.cuh"
 #include "select.cuh"
 
 namespace b200vs {
-
-// Device form of the reference FilterFunctors (src/vector/vector_index.h:67-146), all ANDed.
-struct FilterDev {
-  int has_range;
-  int negate;
-  long long rmin, rmax;
-  const long long* sorted_ids;  // device, ascending
-  long long n_ids;
-};
-
-__device__ __forceinline__ bool filter_pass(const FilterDev& f, long long id) {
-  if (f.has_range && !(id >= f.rmin && id < f.rmax)) return false;  // RangeFilterFunctor::Check
-  if (f.sorted_ids) {                                               // SortFilterFunctor::IsExist
-    long long lo = 0, hi = f.n_ids - 1;
-    bool exist = false;
-    while (lo <= hi) {
-      long long mid = (lo + hi) >> 1;
-      long long v = f.sorted_ids[mid];
-      if (v == id) { exist = true; break; }
-      if (id < v) hi = mid - 1; else lo = mid + 1;
-    }
-    if (f.negate ? exist : !exist) return false;
-  }
-  return true;
-}
 
 struct ScanArgs {
   const float* vecs;        // [rows, d]
@@ -56,6 +32,8 @@ struct ScanArgs {
   int has_thr;         // range search: fixed initial threshold key
   uint32_t thr_key;
   int pool_cap;
+  const int* qmap;    // optional: blockIdx.y -> query index (exact re-run of uncertified queries)
+  const int* qcount;  // optional: number of live entries in qmap (blocks beyond it exit)
 };
 
 constexpr int SCAN_THREADS = 256;
@@ -68,10 +46,15 @@ inline size_t scan_smem_bytes(int d, int nprobe, int pool_cap) {
 }
 
 template <bool L2>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_select_kernel(const ScanArgs a) {
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_select_kernel(const ScanArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int d = a.d;
-  const int qi = blockIdx.y, split = blockIdx.x;
+  const int slot = blockIdx.y, split = blockIdx.x;
+  int qi = slot;
+  if (a.qcount) {
+    if (slot >= *a.qcount) return;
+    qi = a.qmap[slot];
+  }
   float* qs = reinterpret_cast<float*>(smem);
   const size_t qbytes = ((size_t)d * 4 + 15) / 16 * 16;
   int* prefix = reinterpret_cast<int*>(smem + qbytes);
@@ -143,8 +126,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_select_kernel(const ScanArg
   }
   sel.prune();
   const int have = *sel.count;
-  uint32_t* okd = a.ws_kd + ((size_t)qi * a.nsplit + split) * a.k;
-  long long* oki = a.ws_kid + ((size_t)qi * a.nsplit + split) * a.k;
+  uint32_t* okd = a.ws_kd + ((size_t)slot * a.nsplit + split) * a.k;
+  long long* oki = a.ws_kid + ((size_t)slot * a.nsplit + split) * a.k;
   for (int i = threadIdx.x; i < a.k; i += blockDim.x) {
     okd[i] = i < have ? sel.kd[i] : KEY_SENTINEL_D;
     oki[i] = i < have ? sel.kid[i] : KEY_SENTINEL_ID;
@@ -157,17 +140,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_select_kernel(const ScanArg
 //   out_ids : ids, -1 padded                                           [nq, k]
 //   out_counts: valid entries per query                                [nq] or NULL
 template <bool L2>
-__global__ void __launch_bounds__(SCAN_THREADS) merge_select_kernel(const uint32_t* __restrict__ ws_kd,
+static __global__ void __launch_bounds__(SCAN_THREADS) merge_select_kernel(const uint32_t* __restrict__ ws_kd,
                                                                     const long long* __restrict__ ws_kid, int nparts,
                                                                     int k, int pool_cap, float* out_dist, float* out_raw,
-                                                                    long long* out_ids, int* out_counts) {
+                                                                    long long* out_ids, int* out_counts,
+                                                                    const int* qmap, const int* qcount) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int qi = blockIdx.x;
+  const int slot = blockIdx.x;
+  int qi = slot;
+  if (qcount) {
+    if (slot >= *qcount) return;
+    qi = qmap[slot];
+  }
   BlockSelect sel;
   sel.init(smem, pool_cap, k);
   const long long tot = (long long)nparts * k;
-  const uint32_t* kd = ws_kd + (size_t)qi * tot;
-  const long long* kid = ws_kid + (size_t)qi * tot;
+  const uint32_t* kd = ws_kd + (size_t)slot * tot;
+  const long long* kid = ws_kid + (size_t)slot * tot;
   if (nparts == 1) {  // already sorted: copy through
     for (int i = threadIdx.x; i < k; i += blockDim.x) { sel.kd[i] = kd[i]; sel.kid[i] = kid[i]; }
     __syncthreads();
@@ -208,7 +197,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) merge_select_kernel(const uint32
 
 // k-way merge of API-semantics parts [nparts, nq, k] (multi-GPU / sibling-index merge,
 // src/vector/vector_index.cc:1056-1108): ascending distance, ties -> smaller id.
-__global__ void __launch_bounds__(SCAN_THREADS) merge_api_kernel(const float* __restrict__ pd,
+static __global__ void __launch_bounds__(SCAN_THREADS) merge_api_kernel(const float* __restrict__ pd,
                                                                  const long long* __restrict__ pi, int nparts,
                                                                  long long nq, int k, int pool_cap, float* out_dist,
                                                                  long long* out_ids) {
@@ -240,7 +229,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) merge_api_kernel(const float* __
 
 // NormalizeVectorForFaiss (src/vector/vector_index_utils.cc:480-491): n2 = <x,x> (hooked order, the engine's
 // documented choice for the un-vendored faiss::fvec_norm_L2sqr); if n2 > 0 and |1-n2| > 1e-5: x /= sqrt(n2).
-__global__ void normalize_faiss_kernel(float* x, long long n, int d) {
+static __global__ void normalize_faiss_kernel(float* x, long long n, int d) {
   const long long quad = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
   const int t = threadIdx.x & 3;
   const bool valid = quad < n;
@@ -255,7 +244,7 @@ __global__ void normalize_faiss_kernel(float* x, long long n, int d) {
 }
 
 // NormalizeVectorForHnsw (src/vector/vector_index_utils.cc:493-500): sequential scalar sum.
-__global__ void normalize_hnsw_kernel(const float* x, float* out, long long n, int d) {
+static __global__ void normalize_hnsw_kernel(const float* x, float* out, long long n, int d) {
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const float* row = x + (size_t)r * d;
@@ -267,9 +256,9 @@ __global__ void normalize_hnsw_kernel(const float* x, float* out, long long n, i
 }
 
 // Append rows into arena slots: vecs[slot[i]] = src[i], ids[slot[i]] = src_ids[i], norms[slot[i]] = <x,x>.
-__global__ void scatter_rows_kernel(const float* __restrict__ src, const long long* __restrict__ src_ids,
+static __global__ void scatter_rows_kernel(const float* __restrict__ src, const long long* __restrict__ src_ids,
                                     const long long* __restrict__ slots, long long n, int d, float* vecs,
-                                    long long* ids, float* norms) {
+                                    long long* ids, float* norms, float* row_norms) {
   const long long quad = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
   const int t = threadIdx.x & 3;
   const bool valid = quad < n;
@@ -279,11 +268,11 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, const long lo
   const long long s = slots[quad];
   float* dst = vecs + (size_t)s * d;
   for (int i = t; i < d; i += 4) dst[i] = row[i];
-  if (t == 0) { ids[s] = src_ids[quad]; if (norms) norms[s] = n2; }
+  if (t == 0) { ids[s] = src_ids[quad]; if (norms) norms[s] = n2; if (row_norms) row_norms[quad] = n2; }
 }
 
 // Relocate rows (list growth / compaction): dst[dst_rows[i]] = src[src_rows[i]] for vectors, ids, norms.
-__global__ void move_rows_kernel(const float* __restrict__ svecs, const long long* __restrict__ sids,
+static __global__ void move_rows_kernel(const float* __restrict__ svecs, const long long* __restrict__ sids,
                                  const float* __restrict__ snorms, const long long* __restrict__ src_rows,
                                  const long long* __restrict__ dst_rows, long long n, int d, float* dvecs,
                                  long long* dids, float* dnorms) {
@@ -297,12 +286,12 @@ __global__ void move_rows_kernel(const float* __restrict__ svecs, const long lon
   if (lane == 0) { dids[dr] = sids[sr]; if (dnorms) dnorms[dr] = snorms[sr]; }
 }
 
-__global__ void set_ids_kernel(long long* ids, const long long* slots, long long n, long long value) {
+static __global__ void set_ids_kernel(long long* ids, const long long* slots, long long n, long long value) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) ids[slots[i]] = value;
 }
 
-__global__ void iota_kernel(long long* p, long long n) {
+static __global__ void iota_kernel(long long* p, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = i;
 }

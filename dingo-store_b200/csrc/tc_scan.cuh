@@ -15,8 +15,8 @@
 #pragma once
 #include <cuda.h>
 
+#include "filter.cuh"
 #include "index.h"
-#include "scan_kernels.cuh"
 
 namespace b200vs {
 
@@ -69,6 +69,7 @@ struct TcView {
   int64_t total_chunks = 0;     // sum over lists of ceil(len / TC_CHUNK)   (host bookkeeping)
   int max_chunks_per_list = 0;
   float max_norm = 0.f;         // max ||x|| over the index (host bookkeeping, monotone)
+  bool flat = false;            // single list covering rows [0, arena_rows)
 };
 
 // true when this search can use the tensor-core pass (otherwise the caller runs the exact scan)
