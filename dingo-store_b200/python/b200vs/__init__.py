@@ -258,3 +258,10 @@ def ivf_state_blob(centroids, metric):
 
 def merge_topk_device(device, nparts, nq, k, parts_dist_ptr, parts_ids_ptr, out_dist_ptr, out_ids_ptr, stream=None):
     _check(lib().b200vs_merge_topk_device(device, nparts, nq, k, parts_dist_ptr, parts_ids_ptr, out_dist_ptr, out_ids_ptr, stream))
+
+
+def ivfpq_state_blob(centroids, codebooks, metric):
+    """Trained-state blob of an IVF-PQ index: centroids [nlist, d] + codebooks [M, 256, d/M]."""
+    c, cb = _f32(centroids), _f32(codebooks)
+    hdr = np.array([0x51505649, c.shape[0], c.shape[1], metric, cb.shape[0], 8], dtype=np.int64)
+    return np.concatenate([hdr.view(np.uint8), c.reshape(-1).view(np.uint8), cb.reshape(-1).view(np.uint8)])
