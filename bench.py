@@ -283,11 +283,16 @@ def main():
     sampler.start()
     launches[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = os.environ.get("BENCH_PROFILE") == "1"  # ncu --profile-from-start off: only the timed steps are captured
+    if prof:
+        torch.cuda.profiler.start()
     e0.record(stream)
     for i in range(args.steps):
         step_device(i)
     e1.record(stream)
     barrier()
+    if prof:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     gpu_launches = launches[0]
 
