@@ -253,6 +253,16 @@ struct IvfFlatIndex : IndexBase {
   DevBuf<float> norms;           // arena
   IvfLists L;                    // host bookkeeping + device list_off/list_len
   float max_norm = 0.f;
+  float cent_max_norm = 0.f;
+  DevBuf<long long> d_coff;  // the centroid table seen as one "list" by the tensor-core coarse pass
+  DevBuf<int> d_clen;
+  TcView cent_view() const {
+    TcView v;
+    v.vecs = centroids.p; v.ids = cent_ids.p; v.norms = cent_norms.p; v.arena_rows = nlist; v.list_off = d_coff.p; v.list_len = d_clen.p;
+    v.nlist = 1; v.flat = true; v.total_chunks = (nlist + TC_CHUNK - 1) / TC_CHUNK; v.max_chunks_per_list = (int)v.total_chunks;
+    v.max_norm = cent_max_norm;
+    return v;
+  }
   TcView view() const {
     TcView v;
     v.vecs = vecs.p; v.ids = ids.p; v.norms = norms.p; v.arena_rows = L.arena_used; v.list_off = L.d_off.p; v.list_len = L.d_len.p;
@@ -273,6 +283,11 @@ struct IvfFlatIndex : IndexBase {
     cent_norms.reserve(k, 0, stream);
     B200VS_CUDA(cudaMemcpyAsync(centroids.p, host_c, (size_t)k * dim * 4, cudaMemcpyHostToDevice, stream));
     launch_iota(cent_ids.p, k, stream);
+    launch_row_norms(centroids.p, k, dim, cent_norms.p, stream);
+    cent_max_norm = device_max_norm(this, cent_norms.p, k, stream);
+    d_coff.reserve(1, 0, stream); d_clen.reserve(1, 0, stream);
+    B200VS_CUDA(cudaMemsetAsync(d_coff.p, 0, 8, stream));
+    B200VS_CUDA(cudaMemcpyAsync(d_clen.p, &k, 4, cudaMemcpyHostToDevice, stream));
     B200VS_CUDA(cudaStreamSynchronize(stream));
     L.init(k, stream);
     vecs.free(); ids.free(); norms.free();
@@ -335,7 +350,12 @@ struct IvfFlatIndex : IndexBase {
   void range_search_dev(int64_t nq, const float* xq, float radius, int max_results, const SearchCtx& sc, float* od,
                         long long* oi, int* oc, cudaStream_t s) override;
 
-  long long* coarse(int64_t nq, const float* q, int nprobe, cudaStream_t s) {
+  long long* coarse(int64_t nq, const float* q, int nprobe, cudaStream_t s, bool allow_tc = true) {
+    if (allow_tc && tc_coarse_eligible(this, nq, nlist, nprobe)) {  // dense TF32 scores + certified exact re-score
+      long long* probes = scratch.alloc<long long>((size_t)nq * nprobe);
+      tc_coarse(this, cent_view(), metric == B200VS_L2, nq, q, nprobe, probes, nullptr, s);
+      return probes;
+    }
     ScanJob j;
     j.l2 = metric == B200VS_L2;
     j.vecs = centroids.p; j.ids = cent_ids.p; j.d = dim; j.mode = 0; j.n = nlist;
@@ -483,7 +503,7 @@ void IvfFlatIndex::search_dev(int64_t nq, const float* xq, int k, const SearchCt
   if (!trained) { fill_empty_results(nq, k, od, oi, s); return; }  // ivf_flat.cc:224-227
   const float* q = prepare_queries(nq, xq, s);
   const int nprobe = resolve_nprobe(sc);
-  long long* probes = coarse(nq, q, nprobe, s);
+  long long* probes = coarse(nq, q, nprobe, s, !sc.exact_only);
   if (profiling) profile_probed(this, probes, nq * nprobe, nlist, L.d_len.p, s);
   const TcView v = view();
   if (L.live > 0 && tc_eligible(this, v, nq, k, nprobe, sc)) {

@@ -29,7 +29,7 @@ struct IvfLists {
   std::unordered_multimap<int64_t, uint64_t> where;  // id -> (list << 32 | pos)
   int64_t arena_used = 0, arena_used_before = 0, arena_cap = 0;
   int64_t live = 0, dead = 0, garbage = 0;
-  int64_t total_chunks = 0;      // sum of ceil(len / 2048) — tensor-core work-item bound (tc_scan.cuh TC_CHUNK)
+  int64_t total_chunks = 0;      // sum of ceil(len / 512) — tensor-core work-item bound (tc_scan.cuh TC_CHUNK = 512)
   int max_chunks_per_list = 0;
   DevBuf<long long> d_off;
   DevBuf<int> d_len;
@@ -57,7 +57,7 @@ struct IvfLists {
     total_chunks = 0; max_chunks_per_list = 0;
     for (size_t i = 0; i < n; ++i) {
       off[i] = lists[i].off; len[i] = lists[i].len;
-      const int c = (lists[i].len + 2047) / 2048;
+      const int c = (lists[i].len + 511) / 512;
       total_chunks += c; max_chunks_per_list = std::max(max_chunks_per_list, c);
     }
     B200VS_CUDA(cudaMemcpyAsync(d_off.p, off.data(), n * 8, cudaMemcpyHostToDevice, s));

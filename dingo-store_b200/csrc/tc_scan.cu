@@ -5,10 +5,11 @@
 //   tc_count_pairs_kernel    invert the probe table: how many queries probe each list
 //   tc_plan_kernel           exclusive scans -> pair offsets, work-item offsets
 //   tc_fill_pairs_kernel     gather the (TF32-rounded) queries of every list into one contiguous block
-//   tc_items_kernel          emit work items (list chunk x query group)
+//   tc_items_kernel          emit work items (list chunk x query group) + the list of sampled items
 //   tc_scan_kernel           *** the hot kernel: TMA -> smem ring -> tcgen05.mma (TF32) -> TMEM -> epilogue ***
 //   tc_tau_kernel            per-query capture threshold from the sampled rows
 //   tc_final_kernel          per-query window select + exact FP32 (AVX-512 order) rerank + certification
+//   tc_coarse_final_kernel   same for the dense coarse-quantiser scores
 //   tc_compact_flags_kernel  list of uncertified queries for the exact re-run
 #include <algorithm>
 #include <cmath>
@@ -21,11 +22,13 @@ namespace b200vs {
 
 using namespace ptx;
 
+#define TC_INF __int_as_float(0x7f800000)
+
 // ---------------------------------------------------------------------------------------------
 // small helper kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void tc_prep_queries_kernel(const float* __restrict__ q, long long nq, int d, float* __restrict__ q32,
-                                       float* __restrict__ qnorm) {
+static __global__ void tc_prep_queries_kernel(const float* __restrict__ q, long long nq, int d, float* __restrict__ q32,
+                                              float* __restrict__ qnorm) {
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= nq) return;
@@ -44,106 +47,118 @@ __global__ void tc_prep_queries_kernel(const float* __restrict__ q, long long nq
   if (lane == 0) qnorm[w] = acc;
 }
 
-__global__ void tc_count_pairs_kernel(const long long* __restrict__ probes, long long n, int* cnt, int* pos) {
+static __global__ void tc_count_pairs_kernel(const long long* __restrict__ probes, long long n, int* cnt, int* pos) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long l = probes[i];
   pos[i] = l >= 0 ? atomicAdd(cnt + l, 1) : -1;
 }
 
+__device__ __forceinline__ int tc_items_of(int c, int len) {
+  return (c > 0 && len > 0) ? ((c + TC_NQT - 1) / TC_NQT) * ((len + TC_CHUNK - 1) / TC_CHUNK) : 0;
+}
+
 // single block: exclusive scans over the lists
-__global__ void tc_plan_kernel(const int* __restrict__ cnt, const int* __restrict__ list_len, int nlist, int* pair_off,
-                               int* item_off, int* totals /*[0]=n_items [1]=n_pairs*/) {
+static __global__ void tc_plan_kernel(const int* __restrict__ cnt, const int* __restrict__ list_len, int nlist, int* pair_off,
+                                      int* item_off, int* totals /*[0]=n_items [1]=n_pairs [2]=n_sample (zeroed here)*/) {
   __shared__ int s_pairs[1024], s_items[1024];
   const int t = threadIdx.x, T = blockDim.x;
   const int per = (nlist + T - 1) / T;
   const int b = t * per, e = min(nlist, b + per);
   int sp = 0, si = 0;
-  for (int l = b; l < e; ++l) {
-    const int c = cnt[l], len = list_len[l];
-    sp += c;
-    if (c > 0 && len > 0) si += ((c + TC_NQT - 1) / TC_NQT) * ((len + TC_CHUNK - 1) / TC_CHUNK);
-  }
+  for (int l = b; l < e; ++l) { sp += cnt[l]; si += tc_items_of(cnt[l], list_len[l]); }
   s_pairs[t] = sp; s_items[t] = si;
   __syncthreads();
   if (t == 0) {
     int ap = 0, ai = 0;
     for (int i = 0; i < T; ++i) { const int p = s_pairs[i], q = s_items[i]; s_pairs[i] = ap; s_items[i] = ai; ap += p; ai += q; }
-    totals[0] = ai; totals[1] = ap;
+    totals[0] = ai; totals[1] = ap; totals[2] = 0;
   }
   __syncthreads();
   sp = s_pairs[t]; si = s_items[t];
   for (int l = b; l < e; ++l) {
-    const int c = cnt[l], len = list_len[l];
     pair_off[l] = sp; item_off[l] = si;
-    sp += c;
-    if (c > 0 && len > 0) si += ((c + TC_NQT - 1) / TC_NQT) * ((len + TC_CHUNK - 1) / TC_CHUNK);
+    sp += cnt[l]; si += tc_items_of(cnt[l], list_len[l]);
   }
 }
 
 // one warp per (query, probe): place the pair and copy the rounded query row
-__global__ void tc_fill_pairs_kernel(const long long* __restrict__ probes, const int* __restrict__ pos,
-                                     const int* __restrict__ pair_off, long long n, int nprobe, int d,
-                                     const float* __restrict__ q32, int* pair_query, int* pair_of, float* bws) {
+static __global__ void tc_fill_pairs_kernel(const long long* __restrict__ probes, const int* __restrict__ pos,
+                                            const int* __restrict__ pair_off, long long n, int nprobe, int d,
+                                            const float* __restrict__ q32, int* pair_query, float* bws) {
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n) return;
   const long long l = probes[w];
-  if (l < 0) { if (lane == 0) pair_of[w] = -1; return; }
+  if (l < 0) return;
   const int p = pair_off[l] + pos[w];
   const int q = (int)(w / nprobe);
-  if (lane == 0) { pair_query[p] = q; pair_of[w] = p; }
+  if (lane == 0) pair_query[p] = q;
   const float4* src = reinterpret_cast<const float4*>(q32 + (size_t)q * d);
   float4* dst = reinterpret_cast<float4*>(bws + (size_t)p * d);
   for (int i = lane; i < (d >> 2); i += 32) dst[i] = src[i];
 }
 
-__global__ void tc_items_kernel(const int* __restrict__ cnt, const int* __restrict__ list_len,
-                                const int* __restrict__ pair_off, const int* __restrict__ item_off, int nlist, TcItem* items) {
+// items of list l live at item_off[l] + chunk * ngroups + group  (the groups of one chunk are adjacent: the
+// second group re-reads the chunk from L2 while it is hot)
+static __global__ void tc_items_kernel(const int* __restrict__ cnt, const int* __restrict__ list_len,
+                                       const int* __restrict__ pair_off, const int* __restrict__ item_off, int nlist, TcItem* items,
+                                       int* totals, int* sample_list) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= nlist) return;
   const int c = cnt[l], len = list_len[l];
   if (c <= 0 || len <= 0) return;
   const int ng = (c + TC_NQT - 1) / TC_NQT, nc = (len + TC_CHUNK - 1) / TC_CHUNK;
-  TcItem* out = items + item_off[l];
-  for (int g = 0; g < ng; ++g)
-    for (int ch = 0; ch < nc; ++ch) {
+  const int base = item_off[l];
+  for (int ch = 0; ch < nc; ++ch)
+    for (int g = 0; g < ng; ++g) {
       TcItem it;
       it.list = l;
       it.row_begin = ch * TC_CHUNK;
       it.row_end = min(len, (ch + 1) * TC_CHUNK);
       it.pair_begin = pair_off[l] + g * TC_NQT;
       it.nq = min(TC_NQT, c - g * TC_NQT);
-      it.pad[0] = it.pad[1] = it.pad[2] = 0;
-      out[g * nc + ch] = it;
+      it.sample_slot = -1;
+      if ((it.row_begin % TC_SPAN) == 0) {
+        it.sample_slot = atomicAdd(totals + 2, 1);
+        sample_list[it.sample_slot] = base + ch * ng + g;
+      }
+      it.pad[0] = it.pad[1] = 0;
+      items[base + ch * ng + g] = it;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// THE HOT KERNEL.  Persistent, warp-specialised:
-//   warp 0 (one lane): TMA producer  — per K block: A tile = 128 list rows x 32 floats (16 KB, EVICT_FIRST: streamed
-//                      once), B tile = up to 64 gathered queries x 32 floats (8 KB, EVICT_LAST: re-read per tile)
+// THE HOT KERNEL.  Persistent (one CTA per SM), warp-specialised, dynamically scheduled:
+//   warp 0 (one lane): scheduler + TMA producer — claims the next work item with one atomicAdd, publishes it through
+//                      a 4-deep smem queue, then per K block loads the A tile = 128 list rows x 32 floats (16 KB,
+//                      EVICT_FIRST: streamed once) and the B tile = 16/32/64 gathered queries x 32 floats (EVICT_LAST)
 //   warp 1 (one lane): tcgen05.mma issuer — 4 x (M=128, N=16..64, K=8) TF32 MMAs per K block into TMEM
 //   warp 2           : TMEM allocation (2 accumulator buffers x 64 columns)
-//   warps 4-7        : epilogue — tcgen05.ld the 128 x N scores, add ||x||^2, sample / capture
+//   warps 4-7        : epilogue — tcgen05.ld the 128 x N scores, add ||x||^2, then sample / capture / dense store
 // Algorithmic HBM bytes per item: rows x (d*4 + 4 + 8)  (vector, norm, id), read exactly once.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA32,
+               const __grid_constant__ CUtensorMap tmB16, const __grid_constant__ CUtensorMap tmB32,
+               const __grid_constant__ CUtensorMap tmB64, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)TC_STAGES * TC_A_BYTES;
   __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ __align__(8) uint64_t sched_full[TC_SQ], sched_empty[TC_SQ];
+  __shared__ int s_sched[TC_SQ];
   __shared__ uint32_t s_tmem_base;
   __shared__ float s_tau[2][TC_NQT];
   __shared__ int s_q[2][TC_NQT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmA32); prefetch_tmap(&tmB16); prefetch_tmap(&tmB32); prefetch_tmap(&tmB64); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < TC_SQ; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 5); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&s_tmem_base, 2 * TC_NQT);
@@ -151,35 +166,50 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
-  const int n_items = *p.n_items;
+  const int nwork = p.mode == 0 ? p.totals[2] : p.totals[0];
   const int kblocks = (p.d + TC_BK - 1) / TC_BK;
 
   if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer ----------------
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    if (lane == 0) {  // ---------------- scheduler + TMA producer ----------------
+      int stage = 0, slot = 0;
+      uint32_t phase = 0, sphase = 0;
+      for (;;) {
+        mbar_wait(&sched_empty[slot], sphase ^ 1);
+        const int w = atomicAdd(p.work_counter, 1);
+        const int it = w < nwork ? (p.mode == 0 ? p.sample_list[w] : w) : -1;
+        s_sched[slot] = it;
+        mbar_arrive(&sched_full[slot]);
+        if (++slot == TC_SQ) { slot = 0; sphase ^= 1; }
+        if (it < 0) break;
         const TcItem I = p.items[it];
         const long long base_row = p.list_off[I.list] + I.row_begin;
         int rows = I.row_end - I.row_begin;
         if (p.mode == 0) rows = min(rows, TC_SAMPLE);
         const int ntiles = (rows + TC_BM - 1) / TC_BM;
+        const int b_rows = I.nq <= 16 ? 16 : (I.nq <= 32 ? 32 : 64);
+        const CUtensorMap* tb = I.nq <= 16 ? &tmB16 : (I.nq <= 32 ? &tmB32 : &tmB64);
+        const CUtensorMap* ta = p.mode == 0 ? &tmA32 : &tmA;
+        const uint32_t bytes = (p.mode == 0 ? (uint32_t)(TC_SAMPLE * 128) : TC_A_BYTES) + (uint32_t)b_rows * 128u;
         for (int t = 0; t < ntiles; ++t)
           for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], TC_A_BYTES + TC_B_BYTES);
-            tma_load_2d(sA + (size_t)stage * TC_A_BYTES, &tmA, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
-            tma_load_2d(sB + (size_t)stage * TC_B_BYTES, &tmB, &full_bar[stage], kb * TC_BK, I.pair_begin, kEvictLast);
+            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            tma_load_2d(sA + (size_t)stage * TC_A_BYTES, ta, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
+            tma_load_2d(sB + (size_t)stage * TC_B_BYTES, tb, &full_bar[stage], kb * TC_BK, I.pair_begin, kEvictLast);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---------------- MMA issuer ----------------
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t tcount = 0;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      int stage = 0, slot = 0;
+      uint32_t phase = 0, sphase = 0, tcount = 0;
+      for (;;) {
+        mbar_wait(&sched_full[slot], sphase);
+        const int it = s_sched[slot];
+        mbar_arrive(&sched_empty[slot]);
+        if (++slot == TC_SQ) { slot = 0; sphase ^= 1; }
+        if (it < 0) break;
         const TcItem I = p.items[it];
         int rows = I.row_end - I.row_begin;
         if (p.mode == 0) rows = min(rows, TC_SAMPLE);
@@ -210,15 +240,21 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---------------- epilogue: 4 warps, warp ew owns TMEM lanes [32*ew, 32*ew+32) ----------------
     const int ew = warp - 4;
     const int et = threadIdx.x - 128;
-    uint32_t tcount = 0;
-    int icount = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++icount) {
+    uint32_t tcount = 0, sphase = 0;
+    int icount = 0, slot = 0;
+    for (;; ++icount) {
+      mbar_wait(&sched_full[slot], sphase);
+      const int it = s_sched[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sched_empty[slot]);
+      if (++slot == TC_SQ) { slot = 0; sphase ^= 1; }
+      if (it < 0) break;
       const TcItem I = p.items[it];
       const int buf = icount & 1;
       if (et < I.nq) {
         const int q = p.pair_query[I.pair_begin + et];
         s_q[buf][et] = q;
-        s_tau[buf][et] = p.mode ? p.tau[q] : 0.f;
+        s_tau[buf][et] = p.mode == 1 ? p.tau[q] : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const long long list_base = p.list_off[I.list];
@@ -229,7 +265,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int t = 0; t < ntiles; ++t, ++tcount) {
         const uint32_t acc = tcount & 1, aphase = (tcount >> 1) & 1;
         const int r = t * TC_BM + ew * 32 + lane;  // row within the item
-        bool valid = r < rows;
+        const bool inrange = r < rows;
+        bool valid = inrange;
         const long long arow = list_base + I.row_begin + r;
         float nrm = 0.f;
         if (valid) {
@@ -250,12 +287,16 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (n < I.nq) {
               const float dot = __uint_as_float(v[j]);
               const float score = p.l2 ? fmaf(-2.f, dot, nrm) : -dot;
-              if (p.mode == 0) {
-                if (ew == 0 && t == 0) p.sample[((size_t)it * TC_NQT + n) * TC_SAMPLE + lane] = valid ? score : __int_as_float(0x7f800000);
-              } else if (valid && score <= s_tau[buf][n]) {
-                const int q = s_q[buf][n];
-                const int slot = atomicAdd(p.cand_cnt + q, 1);
-                if (slot < p.cap) p.cand[(size_t)q * p.cap + slot] = ((unsigned long long)f2ord(score) << 32) | (unsigned long long)(uint32_t)arow;
+              if (p.mode == 1) {
+                if (valid && score <= s_tau[buf][n]) {
+                  const int q = s_q[buf][n];
+                  const int sl = atomicAdd(p.cand_cnt + q, 1);
+                  if (sl < p.cap) p.cand[(size_t)q * p.cap + sl] = ((unsigned long long)f2ord(score) << 32) | (unsigned long long)(uint32_t)arow;
+                }
+              } else if (p.mode == 0) {
+                if (ew == 0 && t == 0) p.sample[((size_t)I.sample_slot * TC_NQT + n) * TC_SAMPLE + lane] = valid ? score : TC_INF;
+              } else if (inrange) {
+                p.dense[(size_t)s_q[buf][n] * p.dense_ld + (I.row_begin + r)] = valid ? score : TC_INF;
               }
             }
           }
@@ -274,63 +315,87 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // per-query capture threshold: the k-th smallest sampled score (an upper bound of the k-th smallest score overall)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SCAN_THREADS) tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos,
-                                                              const int* __restrict__ pair_of, const int* __restrict__ item_off,
-                                                              const int* __restrict__ list_len, const int* __restrict__ pair_off,
-                                                              int nprobe, const float* __restrict__ sample, int k, int pool_cap,
-                                                              float* tau) {
+constexpr int TAU_PL = 4096;  // (sample slot, column) pairs staged per query
+
+static __global__ void __launch_bounds__(SCAN_THREADS)
+tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos, const int* __restrict__ cnt,
+              const int* __restrict__ item_off, const int* __restrict__ list_len, const TcItem* __restrict__ items, int nprobe,
+              const float* __restrict__ sample, int k, int pool_cap, float* tau) {
   extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int s_np;
   const int q = blockIdx.x;
+  int2* s_pairs = reinterpret_cast<int2*>(smem);  // [TAU_PL]
+  if (threadIdx.x == 0) s_np = 0;
   BlockSelect sel;
-  sel.init(smem, pool_cap, k);
-  // enumerate (probe j, chunk c, sample row s); one thread per sample, SCAN_THREADS at a time
-  for (int j = 0; j < nprobe; ++j) {
+  sel.init(smem + (size_t)TAU_PL * 8, pool_cap, k);  // barrier inside
+  for (int j = threadIdx.x; j < nprobe; j += blockDim.x) {
     const long long l = probes[(size_t)q * nprobe + j];
-    if (l < 0) continue;  // uniform across the block
+    if (l < 0) continue;
     const int len = list_len[l];
     if (len <= 0) continue;
-    const int nc = (len + TC_CHUNK - 1) / TC_CHUNK;
+    const int nc = (len + TC_CHUNK - 1) / TC_CHUNK, ng = (cnt[l] + TC_NQT - 1) / TC_NQT;
     const int ps = pos[(size_t)q * nprobe + j];
     const int g = ps / TC_NQT, n = ps % TC_NQT;
-    const int item0 = item_off[l] + g * nc;
-    const int tot = nc * TC_SAMPLE;
-    for (int base = 0; base < tot; base += blockDim.x) {
-      sel.maybe_prune(blockDim.x);
-      const int i = base + threadIdx.x;
-      if (i < tot) {
-        const int c = i / TC_SAMPLE, s = i % TC_SAMPLE;
-        const float v = sample[((size_t)(item0 + c) * TC_NQT + n) * TC_SAMPLE + s];
-        if (v < __int_as_float(0x7f800000)) {
-          const uint32_t key = f2ord(v);
-          const long long uid = ((long long)(item0 + c) << 8) | s;
-          if (sel.passes(key, uid)) sel.push(key, uid);
-        }
+    const int nspan = (len + TC_SPAN - 1) / TC_SPAN;
+    const int base = atomicAdd(&s_np, nspan);
+    for (int sp = 0; sp < nspan; ++sp) {
+      const int ch = sp * (TC_SPAN / TC_CHUNK);
+      if (ch < nc && base + sp < TAU_PL) s_pairs[base + sp] = make_int2(items[item_off[l] + ch * ng + g].sample_slot, n);
+    }
+  }
+  __syncthreads();
+  const int np_all = s_np;
+  const int np = min(np_all, TAU_PL);
+  const int tot = np * TC_SAMPLE;
+  for (int base = 0; base < tot; base += blockDim.x) {
+    sel.maybe_prune(blockDim.x);
+    const int i = base + threadIdx.x;
+    if (i < tot) {
+      const int2 pr = s_pairs[i / TC_SAMPLE];
+      const int s = i % TC_SAMPLE;
+      const float v = sample[((size_t)pr.x * TC_NQT + pr.y) * TC_SAMPLE + s];
+      if (v < TC_INF) {
+        const uint32_t key = f2ord(v);
+        if (sel.passes(key, i)) sel.push(key, i);
       }
     }
   }
   sel.prune();
-  if (threadIdx.x == 0) tau[q] = (*sel.count >= k) ? ord2f(sel.kd[k - 1]) : __int_as_float(0x7f800000);
+  // more sampled spans than the staging area holds: capture everything (overflow then falls back to the exact scan)
+  if (threadIdx.x == 0) tau[q] = (np_all <= TAU_PL && *sel.count >= k) ? ord2f(sel.kd[k - 1]) : TC_INF;
 }
 
 // ---------------------------------------------------------------------------------------------
 // per query: window select on the approximate scores, exact rerank, certification
 // ---------------------------------------------------------------------------------------------
+constexpr int FIN_SEG = 2048;  // in-window rows staged per round
+
+__device__ __forceinline__ float tc_eps(bool l2, float qnorm_sq, float max_norm, int d) {
+  // rigorous bound on |approx score - exact score|: TF32 truncation of the rows (<= 2^-10 relative), RN rounding of the
+  // query (<= 2^-11), FP32 accumulation; see DESIGN.md
+  const float qn = sqrtf(qnorm_sq);
+  return (l2 ? 2.f : 1.f) * 0.001953125f /*2^-9*/ * qn * max_norm + (float)(d + 64) * 1.1920929e-7f * (qn + max_norm) * (qn + max_norm);
+}
+
 template <bool L2>
-__global__ void __launch_bounds__(SCAN_THREADS)
+static __global__ void __launch_bounds__(SCAN_THREADS)
 tc_final_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int cap,
                 const float* __restrict__ tau, const float* __restrict__ qnorm, float max_norm, const float* __restrict__ q,
                 const float* __restrict__ vecs, const long long* __restrict__ ids, int d, int k, int pool_cap,
                 float* out_dist, long long* out_ids, int* flags) {
   extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int s_m;
   const int qi = blockIdx.x;
   float* qs = reinterpret_cast<float*>(smem);
   const size_t qbytes = ((size_t)d * 4 + 15) / 16 * 16;
+  int* s_rows = reinterpret_cast<int*>(smem + qbytes);  // [FIN_SEG]
+  unsigned char* pool = smem + qbytes + (size_t)FIN_SEG * 4;
   for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = q[(size_t)qi * d + i];
   const int total = cand_cnt[qi];
   const int n = min(total, cap);
   const unsigned long long* c = cand + (size_t)qi * cap;
   BlockSelect sel;
-  sel.init(smem + qbytes, pool_cap, k);
+  sel.init(pool, pool_cap, k);
   // pass 1: k-th smallest approximate score among the captured rows
   for (int base = 0; base < n; base += blockDim.x) {
     sel.maybe_prune(blockDim.x);
@@ -344,38 +409,38 @@ tc_final_kernel(const unsigned long long* __restrict__ cand, const int* __restri
   }
   sel.prune();
   const int have1 = *sel.count;
-  const float inf = __int_as_float(0x7f800000);
-  const float a_k = have1 >= k ? ord2f(sel.kd[k - 1]) : inf;
+  const float a_k = have1 >= k ? ord2f(sel.kd[k - 1]) : TC_INF;
   __syncthreads();
-  // rigorous bound on |approx score - exact score| (TF32 truncation of the rows, RN rounding of the query,
-  // FP32 accumulation), see DESIGN.md
-  const float qn = sqrtf(qnorm[qi]);
-  const float eps = (L2 ? 2.f : 1.f) * 0.001953125f /*2^-9*/ * qn * max_norm + (float)(d + 64) * 1.1920929e-7f * (qn + max_norm) * (qn + max_norm);
-  const float window = a_k + 2.f * eps;  // +inf when fewer than k rows were captured
+  const float window = a_k + 2.f * tc_eps(L2, qnorm[qi], max_norm, d);  // +inf when fewer than k rows were captured
   const float tq = tau[qi];
-  const bool certified = (total <= cap) && (tq == inf || window <= tq);
-  // pass 2: exact distances (reference AVX-512 order) of every captured row inside the window
-  sel.init(smem + qbytes, pool_cap, k);
+  const bool certified = (total <= cap) && (tq == TC_INF || window <= tq);
+  // pass 2: exact distances (reference AVX-512 order) of every captured row inside the window, FIN_SEG at a time
+  sel.init(pool, pool_cap, k);
   const int quad = threadIdx.x >> 2, t = threadIdx.x & 3;
   const bool vec = (d & 3) == 0;
-  for (int base = 0; base < n; base += SCAN_QUADS) {
-    sel.maybe_prune(SCAN_QUADS);
-    const int i = base + quad;
-    bool valid = i < n;
-    long long row = 0;
-    if (valid) {
+  for (int seg = 0; seg < n; seg += FIN_SEG) {
+    if (threadIdx.x == 0) s_m = 0;
+    __syncthreads();
+    const int e1 = min(n, seg + FIN_SEG);
+    for (int i = seg + threadIdx.x; i < e1; i += blockDim.x) {
       const unsigned long long e = c[i];
-      valid = ord2f((uint32_t)(e >> 32)) <= window;
-      row = (long long)(e & 0xffffffffull);
+      if (ord2f((uint32_t)(e >> 32)) <= window) s_rows[atomicAdd(&s_m, 1)] = (int)(uint32_t)(e & 0xffffffffull);
     }
-    if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
-    if (!valid) row = (long long)(c[0] & 0xffffffffull);
-    const float v = quad_distance<L2>(vecs + (size_t)row * d, qs, d, t, vec);
-    if (valid && t == 0) {
-      const uint32_t key = f2ord(L2 ? v : -v);
-      const long long id = ids[row];
-      if (sel.passes(key, id)) sel.push(key, id);
+    __syncthreads();
+    const int m = s_m;
+    for (int base = 0; base < m; base += SCAN_QUADS) {
+      sel.maybe_prune(SCAN_QUADS);
+      const int i = base + quad;
+      const bool valid = i < m;
+      const long long row = (long long)(uint32_t)s_rows[valid ? i : 0];
+      const float v = quad_distance<L2>(vecs + (size_t)row * d, qs, d, t, vec);
+      if (valid && t == 0) {
+        const uint32_t key = f2ord(L2 ? v : -v);
+        const long long id = ids[row];
+        if (sel.passes(key, id)) sel.push(key, id);
+      }
     }
+    __syncthreads();
   }
   sel.prune();
   const int have = *sel.count;
@@ -394,8 +459,68 @@ tc_final_kernel(const unsigned long long* __restrict__ cand, const int* __restri
   if (threadIdx.x == 0) flags[qi] = certified ? 0 : 1;
 }
 
-__global__ void tc_compact_flags_kernel(const int* __restrict__ flags, int nq, int* qmap, int* count) {
-  // single block, order-preserving
+// coarse quantiser: every approximate score is available (dense row), so the window select is always certified
+template <bool L2>
+static __global__ void __launch_bounds__(SCAN_THREADS)
+tc_coarse_final_kernel(const float* __restrict__ dense, long long ld, int nrows, const float* __restrict__ qnorm, float max_norm,
+                       const float* __restrict__ q, const float* __restrict__ vecs, int d, int k, int pool_cap,
+                       long long* out_probes, float* out_raw) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int s_m;
+  const int qi = blockIdx.x;
+  float* qs = reinterpret_cast<float*>(smem);
+  const size_t qbytes = ((size_t)d * 4 + 15) / 16 * 16;
+  int* s_rows = reinterpret_cast<int*>(smem + qbytes);
+  unsigned char* pool = smem + qbytes + (size_t)FIN_SEG * 4;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = q[(size_t)qi * d + i];
+  const float* row_scores = dense + (size_t)qi * ld;
+  BlockSelect sel;
+  sel.init(pool, pool_cap, k);
+  for (int base = 0; base < nrows; base += blockDim.x) {
+    sel.maybe_prune(blockDim.x);
+    const int i = base + threadIdx.x;
+    if (i < nrows) {
+      const float v = row_scores[i];
+      if (v < TC_INF) { const uint32_t key = f2ord(v); if (sel.passes(key, i)) sel.push(key, i); }
+    }
+  }
+  sel.prune();
+  const float a_k = *sel.count >= k ? ord2f(sel.kd[k - 1]) : TC_INF;
+  __syncthreads();
+  const float window = a_k + 2.f * tc_eps(L2, qnorm[qi], max_norm, d);
+  sel.init(pool, pool_cap, k);
+  const int quad = threadIdx.x >> 2, t = threadIdx.x & 3;
+  const bool vec = (d & 3) == 0;
+  for (int seg = 0; seg < nrows; seg += FIN_SEG) {
+    if (threadIdx.x == 0) s_m = 0;
+    __syncthreads();
+    const int e1 = min(nrows, seg + FIN_SEG);
+    for (int i = seg + threadIdx.x; i < e1; i += blockDim.x)
+      if (row_scores[i] <= window) s_rows[atomicAdd(&s_m, 1)] = i;
+    __syncthreads();
+    const int m = s_m;
+    for (int base = 0; base < m; base += SCAN_QUADS) {
+      sel.maybe_prune(SCAN_QUADS);
+      const int i = base + quad;
+      const bool valid = i < m;
+      const int row = s_rows[valid ? i : 0];
+      const float v = quad_distance<L2>(vecs + (size_t)row * d, qs, d, t, vec);
+      if (valid && t == 0) {
+        const uint32_t key = f2ord(L2 ? v : -v);
+        if (sel.passes(key, row)) sel.push(key, row);
+      }
+    }
+    __syncthreads();
+  }
+  sel.prune();
+  const int have = *sel.count;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    out_probes[(size_t)qi * k + i] = i < have ? sel.kid[i] : -1;
+    if (out_raw) { const float v = i < have ? ord2f(sel.kd[i]) : 0.f; out_raw[(size_t)qi * k + i] = L2 ? v : -v; }
+  }
+}
+
+static __global__ void tc_compact_flags_kernel(const int* __restrict__ flags, int nq, int* qmap, int* count) {
   __shared__ int s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
@@ -408,7 +533,7 @@ __global__ void tc_compact_flags_kernel(const int* __restrict__ flags, int nq, i
   if (threadIdx.x == 0) *count = s_cnt;
 }
 
-__global__ void max_norm_kernel(const float* __restrict__ n2, long long n, float* out) {
+static __global__ void max_norm_kernel(const float* __restrict__ n2, long long n, float* out) {
   float m = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = fmaxf(m, n2[i]);
 #pragma unroll
@@ -425,6 +550,20 @@ float device_max_norm(IndexBase* ix, const float* norms_sq, int64_t n, cudaStrea
   B200VS_CUDA(cudaMemcpyAsync(&h, d, 4, cudaMemcpyDeviceToHost, s));
   B200VS_CUDA(cudaStreamSynchronize(s));
   return std::sqrt(h);
+}
+
+static __global__ void row_norms_kernel(const float* __restrict__ x, long long n, int d, float* out) {
+  const long long quad = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const int t = threadIdx.x & 3;
+  const bool valid = quad < n;
+  const float* row = x + (size_t)(valid ? quad : 0) * d;
+  const float n2 = quad_distance<false>(row, row, d, t, (d & 3) == 0);
+  if (valid && t == 0) out[quad] = n2;
+}
+void launch_row_norms(const float* x, int64_t n, int d, float* out, cudaStream_t s) {
+  if (n <= 0) return;
+  row_norms_kernel<<<(unsigned)cdiv(n * 4, 256), 256, 0, s>>>(x, n, d, out);
+  B200VS_CUDA(cudaGetLastError());
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -462,7 +601,23 @@ static CUtensorMap make_tmap(const float* base, int64_t rows, int d, int box_row
 static int64_t tc_item_bound(const TcView& v, int64_t npairs) {
   return (npairs / TC_NQT + 1) * (int64_t)std::max(1, v.max_chunks_per_list) + v.total_chunks;
 }
+static int64_t tc_sample_bound(const TcView& v, int64_t npairs) {  // spans are 4 chunks: at most (chunks + 3) / 4 per list
+  const int64_t max_spans = (v.max_chunks_per_list + 3) / 4 + 1;
+  return (npairs / TC_NQT + 1) * max_spans + (v.total_chunks + 3) / 4 + v.nlist;
+}
 static int tc_cand_cap(int k) { return std::min(16384, std::max(2048, next_pow2(128 * k))); }
+
+static int g_num_sms = 0;
+static void tc_init(int device) {
+  if (g_num_sms) return;
+  B200VS_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, device));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_coarse_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_coarse_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+}
 
 bool tc_eligible(const IndexBase* ix, const TcView& v, int64_t nq, int k, int nprobe, const SearchCtx& sc) {
   if (sc.exact_only) return false;
@@ -472,9 +627,70 @@ bool tc_eligible(const IndexBase* ix, const TcView& v, int64_t nq, int k, int np
   if (!v.norms || !v.vecs) return false;
   const int64_t npairs = nq * nprobe;
   if (npairs >= (1LL << 30)) return false;
-  const int64_t bound = tc_item_bound(v, npairs);
-  if (bound * TC_NQT * TC_SAMPLE * 4 > (2LL << 30)) return false;  // sample buffer too large
+  if (tc_item_bound(v, npairs) >= (1LL << 28)) return false;
+  if (tc_sample_bound(v, npairs) * TC_NQT * TC_SAMPLE * 4 > (2LL << 30)) return false;  // sample buffer too large
   return true;
+}
+
+// everything the passes share: rounded queries, pair inversion, gathered B block, work items, tensor maps
+struct TcPlan {
+  float* q32; float* qnorm;
+  int *cnt, *pos, *pair_off, *item_off, *totals, *pair_query, *sample_list, *work;
+  float* bws;
+  TcItem* items;
+  int64_t bound, sbound, npairs;
+  CUtensorMap tmA, tmA32, tmB16, tmB32, tmB64;
+};
+
+static TcPlan tc_prepare(IndexBase* ix, const TcView& v, int64_t nq, const float* q, const long long* probes, int nprobe, cudaStream_t s) {
+  tc_init(ix->device);
+  const int d = ix->dim;
+  Scratch& S = ix->scratch;
+  TcPlan P;
+  P.npairs = nq * nprobe;
+  P.bound = tc_item_bound(v, P.npairs);
+  P.sbound = tc_sample_bound(v, P.npairs);
+  P.q32 = S.alloc<float>((size_t)nq * d);
+  P.qnorm = S.alloc<float>(nq);
+  P.cnt = S.alloc<int>(v.nlist);
+  P.pos = S.alloc<int>(P.npairs);
+  P.pair_off = S.alloc<int>(v.nlist);
+  P.item_off = S.alloc<int>(v.nlist);
+  P.totals = S.alloc<int>(4);
+  P.work = S.alloc<int>(4);
+  P.pair_query = S.alloc<int>(P.npairs);
+  P.sample_list = S.alloc<int>(P.sbound);
+  P.bws = S.alloc<float>((size_t)(P.npairs + TC_NQT) * d);
+  P.items = S.alloc<TcItem>(P.bound);
+  B200VS_CUDA(cudaMemsetAsync(P.cnt, 0, (size_t)v.nlist * 4, s));
+  B200VS_CUDA(cudaMemsetAsync(P.work, 0, 16, s));
+  tc_prep_queries_kernel<<<(unsigned)cdiv(nq * 32, 256), 256, 0, s>>>(q, nq, d, P.q32, P.qnorm);
+  tc_count_pairs_kernel<<<(unsigned)cdiv(P.npairs, 256), 256, 0, s>>>(probes, P.npairs, P.cnt, P.pos);
+  tc_plan_kernel<<<1, 1024, 0, s>>>(P.cnt, v.list_len, v.nlist, P.pair_off, P.item_off, P.totals);
+  tc_fill_pairs_kernel<<<(unsigned)cdiv(P.npairs * 32, 256), 256, 0, s>>>(probes, P.pos, P.pair_off, P.npairs, nprobe, d, P.q32, P.pair_query, P.bws);
+  tc_items_kernel<<<(unsigned)cdiv(v.nlist, 128), 128, 0, s>>>(P.cnt, v.list_len, P.pair_off, P.item_off, v.nlist, P.items, P.totals, P.sample_list);
+  B200VS_CUDA(cudaGetLastError());
+  P.tmA = make_tmap(v.vecs, v.arena_rows, d, TC_BM);
+  P.tmA32 = make_tmap(v.vecs, v.arena_rows, d, TC_SAMPLE);
+  P.tmB16 = make_tmap(P.bws, P.npairs + TC_NQT, d, 16);
+  P.tmB32 = make_tmap(P.bws, P.npairs + TC_NQT, d, 32);
+  P.tmB64 = make_tmap(P.bws, P.npairs + TC_NQT, d, 64);
+  ix->launch_count(5);
+  return P;
+}
+
+static TcParams tc_params(const TcView& v, const TcPlan& P, int d, bool l2) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.ids = v.ids; p.norms = v.norms; p.list_off = v.list_off; p.d = d; p.items = P.items; p.totals = P.totals;
+  p.sample_list = P.sample_list; p.pair_query = P.pair_query; p.l2 = l2 ? 1 : 0;
+  return p;
+}
+
+static void tc_launch(const TcPlan& P, const TcParams& p, int64_t work_bound, cudaStream_t s) {
+  const int grid = (int)std::min<int64_t>(g_num_sms, std::max<int64_t>(1, work_bound));
+  tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(P.tmA, P.tmA32, P.tmB16, P.tmB32, P.tmB64, p);
+  B200VS_CUDA(cudaGetLastError());
 }
 
 void run_scan_mapped(IndexBase* ix, const ScanJob& job, int64_t nq_max, const int* qmap, const int* qcount, const float* queries,
@@ -483,80 +699,43 @@ void run_scan_mapped(IndexBase* ix, const ScanJob& job, int64_t nq_max, const in
 void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float* q, int k, const long long* probes,
                int nprobe, const SearchCtx& sc, float* out_dist, long long* out_ids, cudaStream_t s) {
   const int d = ix->dim;
-  const int64_t npairs = nq * nprobe;
-  const int64_t bound = tc_item_bound(v, npairs);
   const int cap = tc_cand_cap(k);
   Scratch& S = ix->scratch;
-  float* q32 = S.alloc<float>((size_t)nq * d);
-  float* qnorm = S.alloc<float>(nq);
-  int* cnt = S.alloc<int>(v.nlist);
-  int* pos = S.alloc<int>(npairs);
-  int* pair_off = S.alloc<int>(v.nlist);
-  int* item_off = S.alloc<int>(v.nlist);
-  int* totals = S.alloc<int>(2);
-  int* pair_query = S.alloc<int>(npairs);
-  int* pair_of = S.alloc<int>(npairs);
-  float* bws = S.alloc<float>((size_t)(npairs + TC_NQT) * d);
-  TcItem* items = S.alloc<TcItem>(bound);
-  float* sample = S.alloc<float>((size_t)bound * TC_NQT * TC_SAMPLE);
+  TcPlan P = tc_prepare(ix, v, nq, q, probes, nprobe, s);
+  float* sample = S.alloc<float>((size_t)P.sbound * TC_NQT * TC_SAMPLE);
   float* tau = S.alloc<float>(nq);
   unsigned long long* cand = S.alloc<unsigned long long>((size_t)nq * cap);
   int* cand_cnt = S.alloc<int>(nq);
   int* flags = S.alloc<int>(nq);
   int* qmap = S.alloc<int>(nq);
   int* qcount = S.alloc<int>(1);
-
-  B200VS_CUDA(cudaMemsetAsync(cnt, 0, (size_t)v.nlist * 4, s));
   B200VS_CUDA(cudaMemsetAsync(cand_cnt, 0, (size_t)nq * 4, s));
-  tc_prep_queries_kernel<<<(unsigned)cdiv(nq * 32, 256), 256, 0, s>>>(q, nq, d, q32, qnorm);
-  tc_count_pairs_kernel<<<(unsigned)cdiv(npairs, 256), 256, 0, s>>>(probes, npairs, cnt, pos);
-  tc_plan_kernel<<<1, 1024, 0, s>>>(cnt, v.list_len, v.nlist, pair_off, item_off, totals);
-  tc_fill_pairs_kernel<<<(unsigned)cdiv(npairs * 32, 256), 256, 0, s>>>(probes, pos, pair_off, npairs, nprobe, d, q32, pair_query, pair_of, bws);
-  tc_items_kernel<<<(unsigned)cdiv(v.nlist, 128), 128, 0, s>>>(cnt, v.list_len, pair_off, item_off, v.nlist, items);
-  B200VS_CUDA(cudaGetLastError());
 
-  const CUtensorMap tmA = make_tmap(v.vecs, v.arena_rows, d, TC_BM);
-  const CUtensorMap tmB = make_tmap(bws, npairs + TC_NQT, d, TC_NQT);
-  TcParams p;
-  p.ids = v.ids; p.norms = v.norms; p.list_off = v.list_off; p.d = d; p.items = items; p.n_items = totals;
-  p.pair_query = pair_query; p.sample = sample; p.tau = tau; p.cand = cand; p.cand_cnt = cand_cnt; p.cap = cap;
-  p.l2 = l2 ? 1 : 0;
+  TcParams p = tc_params(v, P, d, l2);
+  p.sample = sample; p.tau = tau; p.cand = cand; p.cand_cnt = cand_cnt; p.cap = cap;
   p.filt.has_range = sc.has_range; p.filt.negate = sc.negate; p.filt.rmin = sc.rmin; p.filt.rmax = sc.rmax;
   p.filt.sorted_ids = sc.sorted_ids_dev; p.filt.n_ids = sc.n_ids;
-
-  static int num_sms = 0;
-  if (!num_sms) {
-    B200VS_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, ix->device));
-    B200VS_CUDA(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-  }
-  const int grid = (int)std::min<int64_t>(num_sms, std::max<int64_t>(1, bound));
   const int pool = select_pool_cap(k, SCAN_THREADS);
   const size_t sel_smem = BlockSelect::smem_bytes(pool);
 
   // 1) sample pass -> per-query capture thresholds
-  p.mode = 0;
-  tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(tmA, tmB, p);
-  B200VS_CUDA(cudaFuncSetAttribute(tc_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, sel_smem, s>>>(probes, pos, pair_of, item_off, v.list_len, pair_off, nprobe, sample, k, pool, tau);
-  // 2) full pass: stream every probed list chunk once, capture rows under the threshold
-  p.mode = 1;
+  p.mode = 0; p.work_counter = P.work;
+  tc_launch(P, p, P.sbound, s);
+  tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, (size_t)TAU_PL * 8 + sel_smem, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, k, pool, tau);
+  // 2) capture pass: stream every probed list chunk once, keep rows under the threshold
+  p.mode = 1; p.work_counter = P.work + 1;
   {
     ScopedKernelTimer timer(ix, s, ix->profiling);
-    tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(tmA, tmB, p);
+    tc_launch(P, p, P.bound, s);
     timer.stop();
   }
   // 3) window select + exact rerank + certification
-  const size_t fin_smem = ((size_t)d * 4 + 15) / 16 * 16 + sel_smem;
-  if (l2) {
-    B200VS_CUDA(cudaFuncSetAttribute(tc_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    tc_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags);
-  } else {
-    B200VS_CUDA(cudaFuncSetAttribute(tc_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    tc_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags);
-  }
+  const size_t fin_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + sel_smem;
+  if (l2) tc_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags);
+  else tc_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags);
   tc_compact_flags_kernel<<<1, 1024, 0, s>>>(flags, (int)nq, qmap, qcount);
   B200VS_CUDA(cudaGetLastError());
-  ix->launch_count(10);
+  ix->launch_count(5);
   ix->stats[1] = nq;
   // 4) uncertified queries re-run on the exact scan (device-side count: blocks beyond it exit immediately)
   ScanJob job;
@@ -570,6 +749,33 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
     B200VS_CUDA(cudaStreamSynchronize(s));
     ix->stats[2] = h;
   }
+}
+
+bool tc_coarse_eligible(const IndexBase* ix, int64_t nq, int nrows, int nprobe) {
+  if (ix->dim % 4 != 0 || ix->dim < 32) return false;
+  if (nq < 16 || nrows < 64 || nprobe > 1024) return false;
+  if ((int64_t)nq * nrows * 4 > (1LL << 30)) return false;  // dense score matrix
+  return true;
+}
+
+void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float* q, int nprobe, long long* out_probes,
+               float* out_raw, cudaStream_t s) {
+  const int d = ix->dim;
+  Scratch& S = ix->scratch;
+  long long* zero_probes = S.alloc<long long>(nq);
+  B200VS_CUDA(cudaMemsetAsync(zero_probes, 0, (size_t)nq * 8, s));
+  TcPlan P = tc_prepare(ix, v, nq, q, zero_probes, 1, s);
+  const int nrows = (int)v.arena_rows;
+  float* dense = S.alloc<float>((size_t)nq * nrows);
+  TcParams p = tc_params(v, P, d, l2);
+  p.mode = 2; p.dense = dense; p.dense_ld = nrows; p.work_counter = P.work;
+  tc_launch(P, p, P.bound, s);
+  const int pool = select_pool_cap(nprobe, SCAN_THREADS);
+  const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + BlockSelect::smem_bytes(pool);
+  if (l2) tc_coarse_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, P.qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
+  else tc_coarse_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, P.qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
+  B200VS_CUDA(cudaGetLastError());
+  ix->launch_count(2);
 }
 
 }  // namespace b200vs

@@ -2,9 +2,10 @@
 //
 // What it replaces: the per-query CPU scans IVFFlatScanner::scan_codes / exhaustive_*_seq behind
 // VectorIndexIvfFlat::Search and VectorIndexFlat::Search (src/vector/vector_index_ivf_flat.cc:247-251,
-// vector_index_flat.cc:249-252).  The reference streams every probed list once PER QUERY on one core; here
-// each probed list (chunk) is streamed from HBM ONCE PER BATCH and multiplied against all queries that probe
-// it — the one place on this path where the work is a dense contraction.
+// vector_index_flat.cc:249-252) and the IndexFlat coarse quantiser of IVF (vector_index_ivf_flat.cc:805-837).
+// The reference streams every probed list once PER QUERY on one core; here each probed list chunk is streamed
+// from HBM ONCE PER BATCH and multiplied against all queries that probe it — the one place on this path where
+// the work is a dense contraction.
 //
 // Exactness: the MMA runs in TF32 (operands truncated to 10 mantissa bits), so its scores only SELECT
 // candidates.  Per query the engine keeps every row whose approximate score is within 2*eps of the k-th best
@@ -20,13 +21,15 @@
 
 namespace b200vs {
 
-constexpr int TC_BM = 128;       // database rows per MMA tile (UMMA M)
-constexpr int TC_BK = 32;        // floats per K block = 128 B = one swizzle span
-constexpr int TC_NQT = 64;       // queries per work item (UMMA N <= 64)
-constexpr int TC_STAGES = 6;     // TMA->MMA ring depth
-constexpr int TC_THREADS = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
-constexpr int TC_CHUNK = 2048;   // rows per work item (list chunk)
-constexpr int TC_SAMPLE = 32;    // sampled rows per chunk for the threshold estimate
+constexpr int TC_BM = 128;        // database rows per MMA tile (UMMA M)
+constexpr int TC_BK = 32;         // floats per K block = 128 B = one swizzle span
+constexpr int TC_NQT = 64;        // queries per work item (UMMA N <= 64)
+constexpr int TC_STAGES = 6;      // TMA->MMA ring depth
+constexpr int TC_THREADS = 256;   // warp0 TMA + scheduler, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
+constexpr int TC_CHUNK = 512;     // rows per work item (list chunk): fine grain for dynamic load balance
+constexpr int TC_SPAN = 2048;     // one sampled chunk per TC_SPAN rows of a list
+constexpr int TC_SAMPLE = 32;     // sampled rows per span for the threshold estimate
+constexpr int TC_SQ = 4;          // scheduler queue depth (items the producer may run ahead)
 constexpr uint32_t TC_A_BYTES = TC_BM * 128;
 constexpr uint32_t TC_B_BYTES = TC_NQT * 128;
 constexpr size_t TC_SMEM = (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024;
@@ -36,7 +39,8 @@ struct TcItem {
   int row_begin, row_end;  // rows within the list
   int pair_begin;          // first row of this item's query group in the gathered-query workspace
   int nq;                  // queries in the group (1..TC_NQT)
-  int pad[3];
+  int sample_slot;         // >= 0 when this item is a sampled chunk
+  int pad[2];
 };
 
 struct TcParams {
@@ -45,14 +49,18 @@ struct TcParams {
   const long long* list_off;
   int d;
   const TcItem* items;
-  const int* n_items;
-  const int* pair_query;  // [npairs] query index of each gathered row
-  int mode;               // 0 = sample pass (dense scores of the first TC_SAMPLE rows), 1 = full pass
-  float* sample;          // [items, TC_NQT, TC_SAMPLE]
-  const float* tau;       // [nq] capture threshold on the approximate score
-  unsigned long long* cand;  // [nq, cap]  (ord(score) << 32 | arena row)
-  int* cand_cnt;             // [nq]
+  const int* totals;        // [0] n_items  [1] n_pairs  [2] n_sample_items
+  const int* sample_list;   // [n_sample_items] item indices
+  int* work_counter;        // dynamic scheduler: next work index
+  const int* pair_query;    // [npairs] query index of each gathered row
+  int mode;                 // 0 = sample pass, 1 = capture pass, 2 = dense pass (every score written)
+  float* sample;            // mode 0: [sample_items, TC_NQT, TC_SAMPLE]
+  const float* tau;         // mode 1: [nq] capture threshold on the approximate score
+  unsigned long long* cand; // mode 1: [nq, cap]  (ord(score) << 32 | arena row)
+  int* cand_cnt;            // mode 1: [nq]
   int cap;
+  float* dense;             // mode 2: [nq, dense_ld] approximate scores (row = column index)
+  long long dense_ld;
   int l2;
   FilterDev filt;
 };
@@ -62,24 +70,32 @@ struct TcView {
   const float* vecs = nullptr;
   const long long* ids = nullptr;
   const float* norms = nullptr;
-  int64_t arena_rows = 0;       // rows addressable by the A tensor map
+  int64_t arena_rows = 0;               // rows addressable by the A tensor map
   const long long* list_off = nullptr;  // device [nlist]
   const int* list_len = nullptr;        // device [nlist]
   int nlist = 0;
-  int64_t total_chunks = 0;     // sum over lists of ceil(len / TC_CHUNK)   (host bookkeeping)
+  int64_t total_chunks = 0;  // sum over lists of ceil(len / TC_CHUNK)   (host bookkeeping)
   int max_chunks_per_list = 0;
-  float max_norm = 0.f;         // max ||x|| over the index (host bookkeeping, monotone)
-  bool flat = false;            // single list covering rows [0, arena_rows)
+  float max_norm = 0.f;      // max ||x|| over the index (host bookkeeping, monotone)
+  bool flat = false;         // single list covering rows [0, arena_rows)
 };
 
 // true when this search can use the tensor-core pass (otherwise the caller runs the exact scan)
 bool tc_eligible(const IndexBase* ix, const TcView& v, int64_t nq, int k, int nprobe, const SearchCtx& sc);
 
 // probes: device [nq, nprobe] list indices (for Flat: all zeros, nprobe = 1).  q: device queries, already
-// normalised for cosine.  Writes API-semantics results.  Falls back per query to the exact scan via `exact`.
+// normalised for cosine.  Writes API-semantics results; uncertified queries are re-run on the exact scan.
 void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float* q, int k, const long long* probes,
                int nprobe, const SearchCtx& sc, float* out_dist, long long* out_ids, cudaStream_t s);
 
+// Exact top-nprobe of every query against a small row set (the IVF coarse quantiser): dense TF32 score matrix on the
+// tensor cores, then window select + exact FP32 re-score.  Always certified (every score is available).
+// out_probes [nq, nprobe] row indices; out_raw (optional) [nq, nprobe] raw metric values (L2 distance / ip).
+bool tc_coarse_eligible(const IndexBase* ix, int64_t nq, int nrows, int nprobe);
+void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float* q, int nprobe, long long* out_probes,
+               float* out_raw, cudaStream_t s);
+
 float device_max_norm(IndexBase* ix, const float* norms_sq, int64_t n, cudaStream_t s);  // sqrt(max ||x||^2)
+void launch_row_norms(const float* x, int64_t n, int d, float* out, cudaStream_t s);     // out[i] = <x_i, x_i>
 
 }  // namespace b200vs
