@@ -137,7 +137,7 @@ def run_reference(args, rank, world):
     order = np.argsort(asg, kind="stable")
     off = np.zeros(nlist + 1, np.int64)
     off[1:] = np.cumsum(np.bincount(asg, minlength=nlist))
-    lx, lids = xb[order], ids[order]
+    lx, lids = o.numa_spread(xb[order], cores), ids[order]
     del xb
     build_s = time.time() - t0
     xq = np.random.default_rng(4321).random((args.batch, d), dtype=np.float32)
@@ -364,6 +364,7 @@ def main():
         o = oracle_lib.load()
         cores = os.cpu_count() or 1
         off, lx, _, lids = ix.export_lists(nlist)
+        lx = o.numa_spread(lx, cores)
         cent = ix.get_trained_state()[32:].view(np.float32).reshape(nlist, d)
         xq = q_host[0].numpy()
         t = time.time()

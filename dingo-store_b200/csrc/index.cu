@@ -254,13 +254,14 @@ struct IvfFlatIndex : IndexBase {
   IvfLists L;                    // host bookkeeping + device list_off/list_len
   float max_norm = 0.f;
   float cent_max_norm = 0.f;
+  DevBuf<float> cent_hi, cent_lo;  // error-compensated split of the centroids (tc_coarse)
   DevBuf<long long> d_coff;  // the centroid table seen as one "list" by the tensor-core coarse pass
   DevBuf<int> d_clen;
   TcView cent_view() const {
     TcView v;
     v.vecs = centroids.p; v.ids = cent_ids.p; v.norms = cent_norms.p; v.arena_rows = nlist; v.list_off = d_coff.p; v.list_len = d_clen.p;
     v.nlist = 1; v.flat = true; v.total_chunks = (nlist + TC_CHUNK - 1) / TC_CHUNK; v.max_chunks_per_list = (int)v.total_chunks;
-    v.max_norm = cent_max_norm;
+    v.max_norm = cent_max_norm; v.vecs_hi = cent_hi.p; v.vecs_lo = cent_lo.p;
     return v;
   }
   TcView view() const {
@@ -284,6 +285,9 @@ struct IvfFlatIndex : IndexBase {
     B200VS_CUDA(cudaMemcpyAsync(centroids.p, host_c, (size_t)k * dim * 4, cudaMemcpyHostToDevice, stream));
     launch_iota(cent_ids.p, k, stream);
     launch_row_norms(centroids.p, k, dim, cent_norms.p, stream);
+    cent_hi.free(); cent_lo.free();
+    cent_hi.reserve((size_t)k * dim, 0, stream); cent_lo.reserve((size_t)k * dim, 0, stream);
+    launch_split_rows(centroids.p, k, dim, cent_hi.p, cent_lo.p, stream);
     cent_max_norm = device_max_norm(this, cent_norms.p, k, stream);
     d_coff.reserve(1, 0, stream); d_clen.reserve(1, 0, stream);
     B200VS_CUDA(cudaMemsetAsync(d_coff.p, 0, 8, stream));

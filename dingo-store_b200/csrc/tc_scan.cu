@@ -47,6 +47,55 @@ static __global__ void tc_prep_queries_kernel(const float* __restrict__ q, long 
   if (lane == 0) qnorm[w] = acc;
 }
 
+// error-compensated operands: hi = TF32 (low 13 mantissa bits cleared / rounded), lo = remainder
+static __global__ void tc_prep_queries_split_kernel(const float* __restrict__ q, long long nq, int d, float* __restrict__ qhi,
+                                                    float* __restrict__ qlo, float* __restrict__ qnorm) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= nq) return;
+  float acc = 0.f;
+  for (int i = lane; i < d; i += 32) {
+    const float v = q[(size_t)w * d + i];
+    acc = fmaf(v, v, acc);
+    uint32_t r, r2;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    const float hi = __uint_as_float(r);
+    const float lo = __fsub_rn(v, hi);  // exact
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r2) : "f"(lo));
+    qhi[(size_t)w * d + i] = hi;
+    qlo[(size_t)w * d + i] = __uint_as_float(r2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) qnorm[w] = acc;
+}
+static __global__ void tc_split_rows_kernel(const float* __restrict__ x, long long n, float* __restrict__ hi, float* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  hi[i] = h;
+  lo[i] = __fsub_rn(v, h);  // exact; the tensor core truncates it to TF32 (error <= 2^-20 |x|)
+}
+void launch_split_rows(const float* x, int64_t n, int d, float* hi, float* lo, cudaStream_t s) {
+  const long long tot = (long long)n * d;
+  if (tot <= 0) return;
+  tc_split_rows_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, s>>>(x, tot, hi, lo);
+  B200VS_CUDA(cudaGetLastError());
+}
+// coarse pass: items = (row chunk) x (query group); B rows are the query rows themselves
+static __global__ void tc_coarse_items_kernel(int nrows, int nq, TcItem* items, int* totals) {
+  const int nc = (nrows + TC_CHUNK - 1) / TC_CHUNK, ng = (nq + TC_NQT - 1) / TC_NQT;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { totals[0] = nc * ng; totals[1] = nq; totals[2] = 0; }
+  if (i >= nc * ng) return;
+  const int ch = i / ng, g = i % ng;
+  TcItem it;
+  it.list = 0; it.row_begin = ch * TC_CHUNK; it.row_end = min(nrows, (ch + 1) * TC_CHUNK);
+  it.pair_begin = g * TC_NQT; it.nq = min(TC_NQT, nq - g * TC_NQT); it.sample_slot = -1; it.pad[0] = it.pad[1] = 0;
+  items[i] = it;
+}
+
 static __global__ void tc_count_pairs_kernel(const long long* __restrict__ probes, long long n, int* cnt, int* pos) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -67,15 +116,29 @@ static __global__ void tc_plan_kernel(const int* __restrict__ cnt, const int* __
   const int b = t * per, e = min(nlist, b + per);
   int sp = 0, si = 0;
   for (int l = b; l < e; ++l) { sp += cnt[l]; si += tc_items_of(cnt[l], list_len[l]); }
-  s_pairs[t] = sp; s_items[t] = si;
+  // block-wide exclusive scan of (sp, si): warp shuffles + one scan of the 32 warp totals
+  const int lane = t & 31, wid = t >> 5;
+  int ip = sp, ii = si;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int vp = __shfl_up_sync(0xffffffffu, ip, o), vi = __shfl_up_sync(0xffffffffu, ii, o);
+    if (lane >= o) { ip += vp; ii += vi; }
+  }
+  if (lane == 31) { s_pairs[wid] = ip; s_items[wid] = ii; }
   __syncthreads();
-  if (t == 0) {
-    int ap = 0, ai = 0;
-    for (int i = 0; i < T; ++i) { const int p = s_pairs[i], q = s_items[i]; s_pairs[i] = ap; s_items[i] = ai; ap += p; ai += q; }
-    totals[0] = ai; totals[1] = ap; totals[2] = 0;
+  if (wid == 0) {
+    int wp = lane < (T >> 5) ? s_pairs[lane] : 0, wi = lane < (T >> 5) ? s_items[lane] : 0;
+    const int tp = wp, ti = wi;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int vp = __shfl_up_sync(0xffffffffu, wp, o), vi = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) { wp += vp; wi += vi; }
+    }
+    if (lane == 31) { totals[0] = wi; totals[1] = wp; totals[2] = 0; }
+    s_pairs[lane] = wp - tp; s_items[lane] = wi - ti;  // exclusive warp offsets
   }
   __syncthreads();
-  sp = s_pairs[t]; si = s_items[t];
+  sp = s_pairs[wid] + ip - sp; si = s_items[wid] + ii - si;  // exclusive prefix of this thread
   for (int l = b; l < e; ++l) {
     pair_off[l] = sp; item_off[l] = si;
     sp += cnt[l]; si += tc_items_of(cnt[l], list_len[l]);
@@ -252,7 +315,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const TcItem I = p.items[it];
       const int buf = icount & 1;
       if (et < I.nq) {
-        const int q = p.pair_query[I.pair_begin + et];
+        const int q = p.pair_query ? p.pair_query[I.pair_begin + et] : I.pair_begin + et;
         s_q[buf][et] = q;
         s_tau[buf][et] = p.mode == 1 ? p.tau[q] : 0.f;
       }
@@ -272,7 +335,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (valid) {
           const long long id = p.ids[arow];
           valid = id >= 0 && filter_pass(p.filt, id);
-          if (valid && p.l2) nrm = p.norms[arow];
+          if (valid && p.l2 && p.add_norm) nrm = p.norms[arow];
         }
         mbar_wait(&tfull_bar[acc], aphase);
         tc_fence_after();
@@ -296,7 +359,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               } else if (p.mode == 0) {
                 if (ew == 0 && t == 0) p.sample[((size_t)I.sample_slot * TC_NQT + n) * TC_SAMPLE + lane] = valid ? score : TC_INF;
               } else if (inrange) {
-                p.dense[(size_t)s_q[buf][n] * p.dense_ld + (I.row_begin + r)] = valid ? score : TC_INF;
+                float* dst = p.dense + (size_t)s_q[buf][n] * p.dense_ld + (I.row_begin + r);
+                if (p.dense_accum) *dst = *dst + score;
+                else *dst = valid ? score : TC_INF;
               }
             }
           }
@@ -370,11 +435,14 @@ tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos,
 // ---------------------------------------------------------------------------------------------
 constexpr int FIN_SEG = 2048;  // in-window rows staged per round
 
-__device__ __forceinline__ float tc_eps(bool l2, float qnorm_sq, float max_norm, int d) {
-  // rigorous bound on |approx score - exact score|: TF32 truncation of the rows (<= 2^-10 relative), RN rounding of the
-  // query (<= 2^-11), FP32 accumulation; see DESIGN.md
+__device__ __forceinline__ float tc_eps(bool l2, float qnorm_sq, float max_norm, int d, bool split) {
+  // rigorous bound on |approx score - exact score|.  Operand term: single-pass TF32 = rows truncated
+  // (<= 2^-10 relative) + query rounded (<= 2^-11) -> 2^-9 with slack; split pass (hi*hi + lo*hi + hi*lo) -> 2^-19.
+  // Accumulation term: FP32 sums of d terms on both sides (tensor core, norms, and the exact kernel itself).
   const float qn = sqrtf(qnorm_sq);
-  return (l2 ? 2.f : 1.f) * 0.001953125f /*2^-9*/ * qn * max_norm + (float)(d + 64) * 1.1920929e-7f * (qn + max_norm) * (qn + max_norm);
+  const float operand = (l2 ? 2.f : 1.f) * (split ? 1.9073486e-6f /*2^-19*/ : 0.001953125f /*2^-9*/) * qn * max_norm;
+  const float accum = 2.f * (float)(d + 64) * 5.9604645e-8f /*2^-24*/ * (l2 ? max_norm * max_norm + 2.f * qn * max_norm : qn * max_norm);
+  return operand + accum;
 }
 
 template <bool L2>
@@ -411,7 +479,7 @@ tc_final_kernel(const unsigned long long* __restrict__ cand, const int* __restri
   const int have1 = *sel.count;
   const float a_k = have1 >= k ? ord2f(sel.kd[k - 1]) : TC_INF;
   __syncthreads();
-  const float window = a_k + 2.f * tc_eps(L2, qnorm[qi], max_norm, d);  // +inf when fewer than k rows were captured
+  const float window = a_k + 2.f * tc_eps(L2, qnorm[qi], max_norm, d, false);  // +inf when fewer than k rows were captured
   const float tq = tau[qi];
   const bool certified = (total <= cap) && (tq == TC_INF || window <= tq);
   // pass 2: exact distances (reference AVX-512 order) of every captured row inside the window, FIN_SEG at a time
@@ -487,7 +555,7 @@ tc_coarse_final_kernel(const float* __restrict__ dense, long long ld, int nrows,
   sel.prune();
   const float a_k = *sel.count >= k ? ord2f(sel.kd[k - 1]) : TC_INF;
   __syncthreads();
-  const float window = a_k + 2.f * tc_eps(L2, qnorm[qi], max_norm, d);
+  const float window = a_k + 2.f * tc_eps(L2, qnorm[qi], max_norm, d, true);
   sel.init(pool, pool_cap, k);
   const int quad = threadIdx.x >> 2, t = threadIdx.x & 3;
   const bool vec = (d & 3) == 0;
@@ -685,7 +753,7 @@ static TcParams tc_params(const TcView& v, const TcPlan& P, int d, bool l2) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.ids = v.ids; p.norms = v.norms; p.list_off = v.list_off; p.d = d; p.items = P.items; p.totals = P.totals;
-  p.sample_list = P.sample_list; p.pair_query = P.pair_query; p.l2 = l2 ? 1 : 0;
+  p.sample_list = P.sample_list; p.pair_query = P.pair_query; p.l2 = l2 ? 1 : 0; p.add_norm = 1;
   return p;
 }
 
@@ -760,24 +828,48 @@ bool tc_coarse_eligible(const IndexBase* ix, int64_t nq, int nrows, int nprobe) 
   return true;
 }
 
+// Error-compensated TF32 (hi*hi + lo*hi + hi*lo): three dense launches accumulate into one score matrix.  The
+// remaining error (<= 2^-19 relative) makes the exact re-score window a handful of rows even when all centroid
+// distances are nearly equal (uniform high-dimensional data).
 void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float* q, int nprobe, long long* out_probes,
                float* out_raw, cudaStream_t s) {
+  tc_init(ix->device);
   const int d = ix->dim;
-  Scratch& S = ix->scratch;
-  long long* zero_probes = S.alloc<long long>(nq);
-  B200VS_CUDA(cudaMemsetAsync(zero_probes, 0, (size_t)nq * 8, s));
-  TcPlan P = tc_prepare(ix, v, nq, q, zero_probes, 1, s);
   const int nrows = (int)v.arena_rows;
+  Scratch& S = ix->scratch;
+  float* qhi = S.alloc<float>((size_t)nq * d);
+  float* qlo = S.alloc<float>((size_t)nq * d);
+  float* qnorm = S.alloc<float>(nq);
+  const int nitems = (int)(cdiv(nrows, TC_CHUNK) * cdiv(nq, TC_NQT));
+  TcItem* items = S.alloc<TcItem>(nitems);
+  int* totals = S.alloc<int>(4);
+  int* work = S.alloc<int>(4);
   float* dense = S.alloc<float>((size_t)nq * nrows);
+  B200VS_CUDA(cudaMemsetAsync(work, 0, 16, s));
+  tc_prep_queries_split_kernel<<<(unsigned)cdiv(nq * 32, 256), 256, 0, s>>>(q, nq, d, qhi, qlo, qnorm);
+  tc_coarse_items_kernel<<<(unsigned)cdiv(nitems, 128), 128, 0, s>>>(nrows, (int)nq, items, totals);
+  TcPlan P;
+  memset(&P, 0, sizeof(P));
+  P.items = items; P.totals = totals;
   TcParams p = tc_params(v, P, d, l2);
-  p.mode = 2; p.dense = dense; p.dense_ld = nrows; p.work_counter = P.work;
-  tc_launch(P, p, P.bound, s);
+  p.mode = 2; p.dense = dense; p.dense_ld = nrows; p.pair_query = nullptr;
+  const CUtensorMap a_hi = make_tmap(v.vecs_hi, nrows, d, TC_BM), a_lo = make_tmap(v.vecs_lo, nrows, d, TC_BM);
+  const float* bsrc[3] = {qhi, qhi, qlo};
+  const CUtensorMap* asrc[3] = {&a_hi, &a_lo, &a_hi};
+  const int grid = (int)std::min<int64_t>(g_num_sms, std::max(1, nitems));
+  for (int pass = 0; pass < 3; ++pass) {
+    const CUtensorMap b16 = make_tmap(bsrc[pass], nq, d, 16), b32 = make_tmap(bsrc[pass], nq, d, 32), b64 = make_tmap(bsrc[pass], nq, d, 64);
+    p.work_counter = work + pass;
+    p.dense_accum = pass > 0; p.add_norm = pass == 0;
+    tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(*asrc[pass], *asrc[pass], b16, b32, b64, p);
+  }
+  B200VS_CUDA(cudaGetLastError());
   const int pool = select_pool_cap(nprobe, SCAN_THREADS);
   const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + BlockSelect::smem_bytes(pool);
-  if (l2) tc_coarse_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, P.qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
-  else tc_coarse_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, P.qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
+  if (l2) tc_coarse_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
+  else tc_coarse_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
   B200VS_CUDA(cudaGetLastError());
-  ix->launch_count(2);
+  ix->launch_count(6);
 }
 
 }  // namespace b200vs

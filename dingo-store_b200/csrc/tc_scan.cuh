@@ -61,6 +61,8 @@ struct TcParams {
   int cap;
   float* dense;             // mode 2: [nq, dense_ld] approximate scores (row = column index)
   long long dense_ld;
+  int dense_accum;          // mode 2: add to the stored score instead of overwriting (split-precision passes 2 and 3)
+  int add_norm;             // include the ||x||^2 term (off for the correction passes)
   int l2;
   FilterDev filt;
 };
@@ -77,6 +79,8 @@ struct TcView {
   int64_t total_chunks = 0;  // sum over lists of ceil(len / TC_CHUNK)   (host bookkeeping)
   int max_chunks_per_list = 0;
   float max_norm = 0.f;      // max ||x|| over the index (host bookkeeping, monotone)
+  const float* vecs_hi = nullptr;  // optional split of the rows for the error-compensated coarse pass:
+  const float* vecs_lo = nullptr;  //   hi = x with the low 13 mantissa bits cleared, lo = x - hi (both exact)
   bool flat = false;         // single list covering rows [0, arena_rows)
 };
 
@@ -97,5 +101,6 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
 
 float device_max_norm(IndexBase* ix, const float* norms_sq, int64_t n, cudaStream_t s);  // sqrt(max ||x||^2)
 void launch_row_norms(const float* x, int64_t n, int d, float* out, cudaStream_t s);     // out[i] = <x_i, x_i>
+void launch_split_rows(const float* x, int64_t n, int d, float* hi, float* lo, cudaStream_t s);
 
 }  // namespace b200vs

@@ -102,6 +102,9 @@ int oracle_hnsw_search(oracle_hnsw*, int64_t nq, const float* xq, int32_t k, int
 int64_t oracle_hnsw_export_size(oracle_hnsw*);
 int oracle_hnsw_export(oracle_hnsw*, void* blob, int64_t len);
 
+/* harness utility: multi-threaded first-touch copy (NUMA-spread pages for the timed CPU baseline) */
+void oracle_parallel_copy(void* dst, const void* src, size_t bytes, int nthreads);
+
 const char* oracle_version(void);
 
 #ifdef __cplusplus

@@ -58,6 +58,17 @@ void rand_perm(std::vector<int64_t>& perm, int64_t n, int64_t seed) {
 
 extern "C" {
 
+// first-touch copy by `nthreads` workers (pages spread over the NUMA nodes the worker threads run on), so the timed
+// CPU scans are not throttled by one memory controller; harness utility, not part of the restated path
+void oracle_parallel_copy(void* dst, const void* src, size_t bytes, int nthreads) {
+  const size_t block = 4u << 20;
+  const int64_t nb = (int64_t)((bytes + block - 1) / block);
+  parallel_for(nb, nthreads, [&](int64_t b) {
+    const size_t off = (size_t)b * block;
+    memcpy((char*)dst + off, (const char*)src + off, std::min(block, bytes - off));
+  });
+}
+
 // test/unit_test/vector/test_vector_index_flat.cc:491-500
 void oracle_fixture_mt19937(int64_t n, int32_t d, float* out) {
   std::mt19937 rng;

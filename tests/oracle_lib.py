@@ -61,7 +61,15 @@ class Oracle:
         L.oracle_hnsw_export_size.restype = i64
         L.oracle_hnsw_export.argtypes = [vp, vp, i64]
         L.oracle_version.restype = ctypes.c_char_p
+        L.oracle_parallel_copy.argtypes = [vp, vp, sz, ctypes.c_int]
         self.L = L
+
+    def numa_spread(self, a, nthreads):
+        """Copy of `a` whose pages are first-touched by `nthreads` workers (spread over the NUMA nodes)."""
+        a = np.ascontiguousarray(a)
+        out = np.empty_like(a)
+        self.L.oracle_parallel_copy(out.ctypes.data, a.ctypes.data, a.nbytes, nthreads)
+        return out
 
     # ---- primitives ----
     def l2sqr(self, x, y):
