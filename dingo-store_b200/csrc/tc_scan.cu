@@ -204,7 +204,9 @@ static __global__ void tc_items_kernel(const int* __restrict__ cnt, const int* _
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA32,
                const __grid_constant__ CUtensorMap tmB16, const __grid_constant__ CUtensorMap tmB32,
-               const __grid_constant__ CUtensorMap tmB64, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmB64, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmBlo16, const __grid_constant__ CUtensorMap tmBlo32,
+               const __grid_constant__ CUtensorMap tmBlo64, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -253,6 +255,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const CUtensorMap* tb = I.nq <= 16 ? &tmB16 : (I.nq <= 32 ? &tmB32 : &tmB64);
         const CUtensorMap* ta = p.mode == 0 ? &tmA32 : &tmA;
         const uint32_t bytes = (p.mode == 0 ? (uint32_t)(TC_SAMPLE * 128) : TC_A_BYTES) + (uint32_t)b_rows * 128u;
+        const CUtensorMap* tbl = I.nq <= 16 ? &tmBlo16 : (I.nq <= 32 ? &tmBlo32 : &tmBlo64);
         for (int t = 0; t < ntiles; ++t)
           for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -260,6 +263,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(sA + (size_t)stage * TC_A_BYTES, ta, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
             tma_load_2d(sB + (size_t)stage * TC_B_BYTES, tb, &full_bar[stage], kb * TC_BK, I.pair_begin, kEvictLast);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            if (p.split) {  // error-compensated pass: the "lo" operands ride in the next ring stage
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[stage], bytes);
+              tma_load_2d(sA + (size_t)stage * TC_A_BYTES, &tmAlo, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
+              tma_load_2d(sB + (size_t)stage * TC_B_BYTES, tbl, &full_bar[stage], kb * TC_BK, I.pair_begin, kEvictLast);
+              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
           }
       }
     }
@@ -292,8 +302,24 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < TC_BK / 8; ++k)  // UMMA K = 8 TF32 = 32 B: advance the start address by 2 (>>4 units)
               umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            const int stage_hi = stage;
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            if (p.split) {  // + lo*hi + hi*lo into the same accumulator
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint64_t adesc_lo = make_desc_k128(smem_u32(sA + (size_t)stage * TC_A_BYTES));
+              const uint64_t bdesc_lo = make_desc_k128(smem_u32(sB + (size_t)stage * TC_B_BYTES));
+#pragma unroll
+              for (int k = 0; k < TC_BK / 8; ++k) {
+                umma_tf32(d_tmem, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc, 1u);
+              }
+              umma_commit(&empty_bar[stage_hi]);
+              umma_commit(&empty_bar[stage]);
+              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            } else {
+              umma_commit(&empty_bar[stage_hi]);  // frees the smem slot when these MMAs retire
+            }
           }
           umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
         }
@@ -381,6 +407,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // per-query capture threshold: the k-th smallest sampled score (an upper bound of the k-th smallest score overall)
 // ---------------------------------------------------------------------------------------------
 constexpr int TAU_PL = 4096;  // (sample slot, column) pairs staged per query
+constexpr int TAU_SORT = 4096;  // sampled scores sorted in one shot when they fit
 
 static __global__ void __launch_bounds__(SCAN_THREADS)
 tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos, const int* __restrict__ cnt,
@@ -412,6 +439,29 @@ tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos,
   const int np_all = s_np;
   const int np = min(np_all, TAU_PL);
   const int tot = np * TC_SAMPLE;
+  if (np_all <= TAU_PL && tot <= TAU_SORT) {  // common case: sort all sampled scores once (bitonic, shared memory)
+    float* vals = reinterpret_cast<float*>(smem + (size_t)TAU_PL * 8);
+    int m = 32;
+    while (m < tot) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      float v = TC_INF;
+      if (i < tot) { const int2 pr = s_pairs[i / TC_SAMPLE]; v = sample[((size_t)pr.x * TC_NQT + pr.y) * TC_SAMPLE + (i % TC_SAMPLE)]; }
+      vals[i] = v;
+    }
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1)
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int i = threadIdx.x; i < (m >> 1); i += blockDim.x) {
+          const int pos = 2 * i - (i & (stride - 1)), j = pos + stride;
+          const bool up = (pos & size) == 0;
+          const float a = vals[pos], b = vals[j];
+          if (up ? b < a : a < b) { vals[pos] = b; vals[j] = a; }
+        }
+        __syncthreads();
+      }
+    if (threadIdx.x == 0) tau[q] = k <= tot ? vals[k - 1] : TC_INF;  // +inf entries (masked rows) sort last
+    return;
+  }
   for (int base = 0; base < tot; base += blockDim.x) {
     sel.maybe_prune(blockDim.x);
     const int i = base + threadIdx.x;
@@ -759,7 +809,7 @@ static TcParams tc_params(const TcView& v, const TcPlan& P, int d, bool l2) {
 
 static void tc_launch(const TcPlan& P, const TcParams& p, int64_t work_bound, cudaStream_t s) {
   const int grid = (int)std::min<int64_t>(g_num_sms, std::max<int64_t>(1, work_bound));
-  tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(P.tmA, P.tmA32, P.tmB16, P.tmB32, P.tmB64, p);
+  tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(P.tmA, P.tmA32, P.tmB16, P.tmB32, P.tmB64, P.tmA, P.tmB16, P.tmB32, P.tmB64, p);
   B200VS_CUDA(cudaGetLastError());
 }
 
@@ -791,7 +841,7 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   // 1) sample pass -> per-query capture thresholds
   p.mode = 0; p.work_counter = P.work;
   tc_launch(P, p, P.sbound, s);
-  tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, (size_t)TAU_PL * 8 + sel_smem, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, k, pool, tau);
+  tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, (size_t)TAU_PL * 8 + std::max(sel_smem, (size_t)TAU_SORT * 4), s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, k, pool, tau);
   // 2) capture pass: stream every probed list chunk once, keep rows under the threshold
   p.mode = 1; p.work_counter = P.work + 1;
   {
@@ -854,22 +904,18 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   TcParams p = tc_params(v, P, d, l2);
   p.mode = 2; p.dense = dense; p.dense_ld = nrows; p.pair_query = nullptr;
   const CUtensorMap a_hi = make_tmap(v.vecs_hi, nrows, d, TC_BM), a_lo = make_tmap(v.vecs_lo, nrows, d, TC_BM);
-  const float* bsrc[3] = {qhi, qhi, qlo};
-  const CUtensorMap* asrc[3] = {&a_hi, &a_lo, &a_hi};
+  const CUtensorMap b16 = make_tmap(qhi, nq, d, 16), b32 = make_tmap(qhi, nq, d, 32), b64 = make_tmap(qhi, nq, d, 64);
+  const CUtensorMap l16 = make_tmap(qlo, nq, d, 16), l32 = make_tmap(qlo, nq, d, 32), l64 = make_tmap(qlo, nq, d, 64);
   const int grid = (int)std::min<int64_t>(g_num_sms, std::max(1, nitems));
-  for (int pass = 0; pass < 3; ++pass) {
-    const CUtensorMap b16 = make_tmap(bsrc[pass], nq, d, 16), b32 = make_tmap(bsrc[pass], nq, d, 32), b64 = make_tmap(bsrc[pass], nq, d, 64);
-    p.work_counter = work + pass;
-    p.dense_accum = pass > 0; p.add_norm = pass == 0;
-    tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(*asrc[pass], *asrc[pass], b16, b32, b64, p);
-  }
+  p.work_counter = work; p.split = 1; p.dense_accum = 0; p.add_norm = 1;
+  tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(a_hi, a_hi, b16, b32, b64, a_lo, l16, l32, l64, p);
   B200VS_CUDA(cudaGetLastError());
   const int pool = select_pool_cap(nprobe, SCAN_THREADS);
   const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + BlockSelect::smem_bytes(pool);
   if (l2) tc_coarse_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
   else tc_coarse_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
   B200VS_CUDA(cudaGetLastError());
-  ix->launch_count(6);
+  ix->launch_count(4);
 }
 
 }  // namespace b200vs

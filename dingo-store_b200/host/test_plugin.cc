@@ -101,7 +101,7 @@ static void test_flat() {
     EXPECT(results[0].vector_with_distances_size() == n - 1);  // fewer than k hits -> shorter list
     // range search
     results.clear();
-    EXPECT(ix->RangeSearch({vs[0]}, metric == pb::common::METRIC_TYPE_L2 ? 1e9f : -1e9f, {}, false, sp, results).ok());
+    EXPECT(ix->RangeSearch({vs[0]}, 1e9f, {}, false, sp, results).ok());  // radius is in API distance semantics (1 - ip for IP / cosine)
     EXPECT(results.size() == 1 && results[0].vector_with_distances_size() == n - 1);
     EXPECT(!ix->SupportSave() && !ix->NeedToSave(20000) && !ix->NeedTrain() && ix->IsTrained());
   }
