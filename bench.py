@@ -223,7 +223,7 @@ def main():
         cq = b200vs.Index(b200vs.FLAT, b200vs.L2, d, device=local_rank)  # coarse quantiser as a Flat index over centroids
         cq.add(cent, np.arange(nlist, dtype=np.int64))
         for a, x in chunks:
-            _, lst = cq.search(x, 1)
+            lst = np.concatenate([cq.search(x[b:b + 32768], 1)[1] for b in range(0, x.shape[0], 32768)], 0)
             owner = torch.from_numpy((lst[:, 0] // nlist_local).astype(np.int64))
             order = torch.argsort(owner, stable=True)
             counts = torch.bincount(owner, minlength=world)

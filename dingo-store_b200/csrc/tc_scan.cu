@@ -84,14 +84,14 @@ void launch_split_rows(const float* x, int64_t n, int d, float* hi, float* lo, c
   B200VS_CUDA(cudaGetLastError());
 }
 // coarse pass: items = (row chunk) x (query group); B rows are the query rows themselves
-static __global__ void tc_coarse_items_kernel(int nrows, int nq, TcItem* items, int* totals) {
-  const int nc = (nrows + TC_CHUNK - 1) / TC_CHUNK, ng = (nq + TC_NQT - 1) / TC_NQT;
+static __global__ void tc_coarse_items_kernel(int nrows, int nq, int chunk, TcItem* items, int* totals) {
+  const int nc = (nrows + chunk - 1) / chunk, ng = (nq + TC_NQT - 1) / TC_NQT;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) { totals[0] = nc * ng; totals[1] = nq; totals[2] = 0; }
   if (i >= nc * ng) return;
   const int ch = i / ng, g = i % ng;
   TcItem it;
-  it.list = 0; it.row_begin = ch * TC_CHUNK; it.row_end = min(nrows, (ch + 1) * TC_CHUNK);
+  it.list = 0; it.row_begin = ch * chunk; it.row_end = min(nrows, (ch + 1) * chunk);
   it.pair_begin = g * TC_NQT; it.nq = min(TC_NQT, nq - g * TC_NQT); it.sample_slot = -1; it.pad[0] = it.pad[1] = 0;
   items[i] = it;
 }
@@ -495,6 +495,146 @@ __device__ __forceinline__ float tc_eps(bool l2, float qnorm_sq, float max_norm,
   return operand + accum;
 }
 
+// ---- block-wide bitonic sorts in shared memory (ascending), m = power of two ----
+__device__ __forceinline__ void block_sort_u64(unsigned long long* keys, int m) {
+  for (int size = 2; size <= m; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (m >> 1); i += blockDim.x) {
+        const int pos = 2 * i - (i & (stride - 1)), j = pos + stride;
+        const unsigned long long a = keys[pos], b = keys[j];
+        if (((pos & size) == 0) ? (b < a) : (a < b)) { keys[pos] = b; keys[j] = a; }
+      }
+      __syncthreads();
+    }
+}
+__device__ __forceinline__ void block_sort_pair(uint32_t* kd, long long* kid, int m) {
+  for (int size = 2; size <= m; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < (m >> 1); i += blockDim.x) {
+        const int pos = 2 * i - (i & (stride - 1)), j = pos + stride;
+        const uint32_t ad = kd[pos], bd = kd[j];
+        const long long ai = kid[pos], bi = kid[j];
+        const bool swap = ((pos & size) == 0) ? key_less(bd, bi, ad, ai) : key_less(ad, ai, bd, bi);
+        if (swap) { kd[pos] = bd; kd[j] = ad; kid[pos] = bi; kid[j] = ai; }
+      }
+      __syncthreads();
+    }
+}
+
+// Fast window select shared by the list-scan finish and the coarse finish.  keys[0..n) = (ord(approx score) << 32 | row),
+// unsorted, padded storage for the next power of two.  Sorts once, takes the k-th approximate score, re-scores the
+// in-window prefix exactly (reference order) and returns the exact top-k in (ex_kd, ex_id)[0..k).
+// Returns the number of exact entries kept (<= k) and whether the prefix fit in `maxw`.
+template <bool L2, bool ROW_IS_ID>
+__device__ int window_select(unsigned long long* keys, int n, int k, float two_eps, const float* qs, const float* __restrict__ vecs,
+                             const long long* __restrict__ ids, int d, uint32_t* ex_kd, long long* ex_id, int maxw, bool* fits,
+                             float* a_k_out, int* s_m) {
+  int m2 = 2;
+  while (m2 < n) m2 <<= 1;
+  for (int i = n + threadIdx.x; i < m2; i += blockDim.x) keys[i] = ~0ull;
+  __syncthreads();
+  block_sort_u64(keys, m2);
+  const float a_k = n >= k ? ord2f((uint32_t)(keys[k - 1] >> 32)) : TC_INF;
+  const float window = a_k + two_eps;
+  if (threadIdx.x == 0) *s_m = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {  // sorted: the in-window rows are a prefix
+    const bool in = ord2f((uint32_t)(keys[i] >> 32)) <= window;
+    const bool next_in = (i + 1 < n) && ord2f((uint32_t)(keys[i + 1] >> 32)) <= window;
+    if (in && !next_in) *s_m = i + 1;
+  }
+  __syncthreads();
+  int m = *s_m;
+  *fits = m <= maxw;
+  m = min(m, maxw);
+  *a_k_out = a_k;
+  const int quad = threadIdx.x >> 2, t = threadIdx.x & 3;
+  const bool vec = (d & 3) == 0;
+  for (int base = 0; base < m; base += SCAN_QUADS) {
+    const int i = base + quad;
+    const bool valid = i < m;
+    const long long row = (long long)(uint32_t)(keys[valid ? i : 0] & 0xffffffffull);
+    const float v = quad_distance<L2>(vecs + (size_t)row * d, qs, d, t, vec);
+    if (valid && t == 0) { ex_kd[i] = f2ord(L2 ? v : -v); ex_id[i] = ROW_IS_ID ? row : ids[row]; }
+  }
+  int e2 = 2;
+  while (e2 < m) e2 <<= 1;
+  __syncthreads();
+  for (int i = m + threadIdx.x; i < e2; i += blockDim.x) { ex_kd[i] = KEY_SENTINEL_D; ex_id[i] = KEY_SENTINEL_ID; }
+  __syncthreads();
+  block_sort_pair(ex_kd, ex_id, e2);
+  return min(m, k);
+}
+
+constexpr int FIN_MAXW = 1024;     // in-window rows re-scored per query on the fast path (more -> exact re-run)
+constexpr int COARSE_FAST = 4096;  // coarse rows handled by the one-sort path
+
+template <bool L2>
+static __global__ void __launch_bounds__(SCAN_THREADS)
+tc_final_fast_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int cap,
+                     const float* __restrict__ tau, const float* __restrict__ qnorm, float max_norm, const float* __restrict__ q,
+                     const float* __restrict__ vecs, const long long* __restrict__ ids, int d, int k, float* out_dist,
+                     long long* out_ids, int* flags) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int s_m;
+  const int qi = blockIdx.x;
+  float* qs = reinterpret_cast<float*>(smem);
+  const size_t qbytes = ((size_t)d * 4 + 15) / 16 * 16;
+  long long* ex_id = reinterpret_cast<long long*>(smem + qbytes);                    // [FIN_MAXW]
+  uint32_t* ex_kd = reinterpret_cast<uint32_t*>(smem + qbytes + (size_t)FIN_MAXW * 8);  // [FIN_MAXW]
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + qbytes + (size_t)FIN_MAXW * 12);  // [pow2(cap)]
+  for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = q[(size_t)qi * d + i];
+  const int total = cand_cnt[qi];
+  const int n = min(total, cap);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = cand[(size_t)qi * cap + i];
+  __syncthreads();
+  bool fits;
+  float a_k;
+  const float two_eps = 2.f * tc_eps(L2, qnorm[qi], max_norm, d, false);
+  const int have = window_select<L2, false>(keys, n, k, two_eps, qs, vecs, ids, d, ex_kd, ex_id, FIN_MAXW, &fits, &a_k, &s_m);
+  const float tq = tau[qi];
+  const bool certified = fits && (total <= cap) && (tq == TC_INF || a_k + two_eps <= tq);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    float api = 0.f;
+    long long id = -1;
+    if (i < have) {
+      const float v = ord2f(ex_kd[i]);
+      const float raw = L2 ? v : -v;
+      api = L2 ? raw : __fsub_rn(1.0f, raw);
+      id = ex_id[i];
+    }
+    out_dist[(size_t)qi * k + i] = api;
+    out_ids[(size_t)qi * k + i] = id;
+  }
+  if (threadIdx.x == 0) flags[qi] = certified ? 0 : 1;
+}
+
+template <bool L2>
+static __global__ void __launch_bounds__(SCAN_THREADS)
+tc_coarse_final_fast_kernel(const float* __restrict__ dense, long long ld, int nrows, const float* __restrict__ qnorm, float max_norm,
+                            const float* __restrict__ q, const float* __restrict__ vecs, int d, int k, long long* out_probes,
+                            float* out_raw) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ int s_m;
+  const int qi = blockIdx.x;
+  float* qs = reinterpret_cast<float*>(smem);
+  const size_t qbytes = ((size_t)d * 4 + 15) / 16 * 16;
+  long long* ex_id = reinterpret_cast<long long*>(smem + qbytes);                              // [COARSE_FAST]
+  uint32_t* ex_kd = reinterpret_cast<uint32_t*>(smem + qbytes + (size_t)COARSE_FAST * 8);      // [COARSE_FAST]
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + qbytes + (size_t)COARSE_FAST * 12);  // [COARSE_FAST]
+  for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = q[(size_t)qi * d + i];
+  for (int i = threadIdx.x; i < nrows; i += blockDim.x) keys[i] = ((unsigned long long)f2ord(dense[(size_t)qi * ld + i]) << 32) | (unsigned)i;
+  __syncthreads();
+  bool fits;
+  float a_k;
+  const float two_eps = 2.f * tc_eps(L2, qnorm[qi], max_norm, d, true);
+  const int have = window_select<L2, true>(keys, nrows, k, two_eps, qs, vecs, nullptr, d, ex_kd, ex_id, COARSE_FAST, &fits, &a_k, &s_m);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    out_probes[(size_t)qi * k + i] = i < have ? ex_id[i] : -1;
+    if (out_raw) { const float v = i < have ? ord2f(ex_kd[i]) : 0.f; out_raw[(size_t)qi * k + i] = L2 ? v : -v; }
+  }
+}
+
 template <bool L2>
 static __global__ void __launch_bounds__(SCAN_THREADS)
 tc_final_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int cap,
@@ -736,6 +876,10 @@ static void tc_init(int device) {
   B200VS_CUDA(cudaFuncSetAttribute(tc_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));  // + static smem
   B200VS_CUDA(cudaFuncSetAttribute(tc_coarse_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));  // + static smem
   B200VS_CUDA(cudaFuncSetAttribute(tc_coarse_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));  // + static smem
+  B200VS_CUDA(cudaFuncSetAttribute(tc_final_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_final_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_coarse_final_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_coarse_final_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   g_num_sms = sms;  // only after every attribute call succeeded
 }
 
@@ -850,9 +994,15 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
     timer.stop();
   }
   // 3) window select + exact rerank + certification
-  const size_t fin_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + sel_smem;
-  if (l2) tc_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags);
-  else tc_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags);
+  const size_t fast_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_MAXW * 12 + (size_t)next_pow2(cap) * 8;
+  if (fast_smem <= 200 * 1024) {  // one 64-bit sort of the captured rows + a small exact sort
+    if (l2) tc_final_fast_kernel<true><<<(unsigned)nq, SCAN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
+    else tc_final_fast_kernel<false><<<(unsigned)nq, SCAN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
+  } else {
+    const size_t fin_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + sel_smem;
+    if (l2) tc_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags);
+    else tc_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags);
+  }
   tc_compact_flags_kernel<<<1, 1024, 0, s>>>(flags, (int)nq, qmap, qcount);
   B200VS_CUDA(cudaGetLastError());
   ix->launch_count(5);
@@ -890,14 +1040,15 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   float* qhi = S.alloc<float>((size_t)nq * d);
   float* qlo = S.alloc<float>((size_t)nq * d);
   float* qnorm = S.alloc<float>(nq);
-  const int nitems = (int)(cdiv(nrows, TC_CHUNK) * cdiv(nq, TC_NQT));
+  const int chunk = nrows <= 16384 ? TC_BM : TC_CHUNK;  // small tables: one tile per item so the whole chip has work
+  const int nitems = (int)(cdiv(nrows, chunk) * cdiv(nq, TC_NQT));
   TcItem* items = S.alloc<TcItem>(nitems);
   int* totals = S.alloc<int>(4);
   int* work = S.alloc<int>(4);
   float* dense = S.alloc<float>((size_t)nq * nrows);
   B200VS_CUDA(cudaMemsetAsync(work, 0, 16, s));
   tc_prep_queries_split_kernel<<<(unsigned)cdiv(nq * 32, 256), 256, 0, s>>>(q, nq, d, qhi, qlo, qnorm);
-  tc_coarse_items_kernel<<<(unsigned)cdiv(nitems, 128), 128, 0, s>>>(nrows, (int)nq, items, totals);
+  tc_coarse_items_kernel<<<(unsigned)cdiv(nitems, 128), 128, 0, s>>>(nrows, (int)nq, chunk, items, totals);
   TcPlan P;
   memset(&P, 0, sizeof(P));
   P.items = items; P.totals = totals;
@@ -910,10 +1061,16 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   p.work_counter = work; p.split = 1; p.dense_accum = 0; p.add_norm = 1;
   tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(a_hi, a_hi, b16, b32, b64, a_lo, l16, l32, l64, p);
   B200VS_CUDA(cudaGetLastError());
-  const int pool = select_pool_cap(nprobe, SCAN_THREADS);
-  const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + BlockSelect::smem_bytes(pool);
-  if (l2) tc_coarse_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
-  else tc_coarse_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
+  if (nrows <= COARSE_FAST && nprobe <= nrows) {
+    const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)COARSE_FAST * 20;
+    if (l2) tc_coarse_final_fast_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, out_probes, out_raw);
+    else tc_coarse_final_fast_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, out_probes, out_raw);
+  } else {
+    const int pool = select_pool_cap(nprobe, SCAN_THREADS);
+    const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + BlockSelect::smem_bytes(pool);
+    if (l2) tc_coarse_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
+    else tc_coarse_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
+  }
   B200VS_CUDA(cudaGetLastError());
   ix->launch_count(4);
 }
