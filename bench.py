@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exact-only", action="store_true", help="force the exact FP32 scan path")
+    ap.add_argument("--in-flight", type=int, default=2, help="batches in flight (streams / caller threads); the reference serves "
+                    "searches from a 16-thread pool, so concurrent batches are the deployed shape")
     return ap.parse_args()
 
 
@@ -171,7 +173,7 @@ def workload_config(args, world):
     return {"workload": f"IVF-Flat L2 {args.nb}x{args.dim} f32 per GPU, nlist={args.nlist} per GPU, nprobe={args.nprobe}, "
                         f"batch={args.batch} per GPU, top-{args.k} (BASELINE configs[1] at the metric's batch 1024)",
             "index": "IVF_FLAT", "metric_type": "L2", "nb_per_gpu": args.nb, "dim": args.dim, "nlist_per_gpu": args.nlist,
-            "nprobe": args.nprobe, "batch_per_gpu": args.batch, "topk": args.k,
+            "nprobe": args.nprobe, "batch_per_gpu": args.batch, "topk": args.k, "batches_in_flight": args.in_flight,
             "parallelism": f"list-sharded x{world}, 1 all_gather + merge" if world > 1 else "single GPU",
             "l2_flush": "inputs larger than L2: every step streams the probed lists (~3.1 GB per GPU >> 126 MB L2)"}
 
@@ -248,28 +250,49 @@ def main():
     gq.manual_seed(4321)
     nbatches = 4
     q_dev = [torch.rand((nq, d), generator=gq, device=dev, dtype=torch.float32) for _ in range(nbatches)]
-    out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    L = max(1, args.in_flight)
+    out_d = [torch.empty((nq, k), dtype=torch.float32, device=dev) for _ in range(L)]
+    out_i = [torch.empty((nq, k), dtype=torch.int64, device=dev) for _ in range(L)]
     sp, _keep = b200vs.make_search_params(nprobe=args.nprobe, exact_only=args.exact_only)
-    stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream: the library launches on it and the events time it
-    torch.cuda.set_stream(stream)
+    main_stream = torch.cuda.Stream(device=dev)  # real (non-NULL) streams: the library launches on them, the events time them
+    streams = [torch.cuda.Stream(device=dev) for _ in range(L)]
+    torch.cuda.set_stream(main_stream)
+    stream = streams[0]
     if world > 1:
-        g_d = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
-        g_i = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
-        m_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        m_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        g_d = [torch.empty((world, nq, k), dtype=torch.float32, device=dev) for _ in range(L)]
+        g_i = [torch.empty((world, nq, k), dtype=torch.int64, device=dev) for _ in range(L)]
+        m_d = [torch.empty((nq, k), dtype=torch.float32, device=dev) for _ in range(L)]
+        m_i = [torch.empty((nq, k), dtype=torch.int64, device=dev) for _ in range(L)]
 
     launches = [0]
 
-    def step_device(i):
+    def step_device(i, lanes=L):
+        ln = i % lanes
+        st = streams[ln]
         q = q_dev[i % nbatches]
-        ix.search_device(nq, q.data_ptr(), k, out_d.data_ptr(), out_i.data_ptr(), stream=stream.cuda_stream, sp=sp)
+        ix.search_device(nq, q.data_ptr(), k, out_d[ln].data_ptr(), out_i[ln].data_ptr(), stream=st.cuda_stream, sp=sp)
         launches[0] += ix.stats()[0]
         if world > 1:
-            dist.all_gather_into_tensor(g_d.view(-1), out_d.view(-1))
-            dist.all_gather_into_tensor(g_i.view(-1), out_i.view(-1))
-            b200vs.merge_topk_device(local_rank, world, nq, k, g_d.data_ptr(), g_i.data_ptr(), m_d.data_ptr(), m_i.data_ptr(), stream.cuda_stream)
+            with torch.cuda.stream(st):
+                dist.all_gather_into_tensor(g_d[ln].view(-1), out_d[ln].view(-1))
+                dist.all_gather_into_tensor(g_i[ln].view(-1), out_i[ln].view(-1))
+            b200vs.merge_topk_device(local_rank, world, nq, k, g_d[ln].data_ptr(), g_i[ln].data_ptr(), m_d[ln].data_ptr(), m_i[ln].data_ptr(), st.cuda_stream)
             launches[0] += 1
+
+    def timed_device(steps, lanes):
+        """K steps on `lanes` streams; CUDA events on main_stream bracket all of them."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main_stream)
+        for st in streams[:lanes]:
+            st.wait_event(e0)
+        for i in range(steps):
+            step_device(i, lanes)
+        for st in streams[:lanes]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main_stream.wait_event(ev)
+        e1.record(main_stream)
+        return e0, e1
 
     def barrier():
         if world > 1:
@@ -282,57 +305,69 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches[0] = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     prof = os.environ.get("BENCH_PROFILE") == "1"  # ncu --profile-from-start off: only the timed steps are captured
     if prof:
         torch.cuda.profiler.start()
-    e0.record(stream)
-    for i in range(args.steps):
-        step_device(i)
-    e1.record(stream)
+    e0, e1 = timed_device(args.steps, L)
     barrier()
     if prof:
         torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     gpu_launches = launches[0]
+    # the same K steps strictly one after another on one stream (per-batch latency view)
+    e0, e1 = timed_device(args.steps, 1)
+    barrier()
+    ms_single = e0.elapsed_time(e1)
 
     # ---- e2e: host buffers through the public C-ABI call, copies inside the timed region ----
     q_host = [q.cpu().pin_memory() for q in q_dev]
-    hd = torch.empty((nq, k), dtype=torch.float32).pin_memory()
-    hi = torch.empty((nq, k), dtype=torch.int64).pin_memory()
-    if world > 1:
-        hd_all = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    hd = [torch.empty((nq, k), dtype=torch.float32).pin_memory() for _ in range(L)]
+    hi = [torch.empty((nq, k), dtype=torch.int64).pin_memory() for _ in range(L)]
 
-    def step_e2e(i):
+    def step_e2e(i, ln=0):
         q = q_host[i % nbatches]
         if world == 1:
-            ix.search_raw(nq, q.data_ptr(), k, hd.data_ptr(), hi.data_ptr(), sp=sp)
-            return float(hd[0, 0])
-        qd = q.to(dev, non_blocking=True)
-        ix.search_device(nq, qd.data_ptr(), k, out_d.data_ptr(), out_i.data_ptr(), stream=stream.cuda_stream, sp=sp)
-        dist.all_gather_into_tensor(g_d.view(-1), out_d.view(-1))
-        dist.all_gather_into_tensor(g_i.view(-1), out_i.view(-1))
-        b200vs.merge_topk_device(local_rank, world, nq, k, g_d.data_ptr(), g_i.data_ptr(), m_d.data_ptr(), m_i.data_ptr(), stream.cuda_stream)
-        hd_all.copy_(m_d, non_blocking=True)
-        hi.copy_(m_i, non_blocking=True)
-        torch.cuda.synchronize()
-        return float(hd_all[0, 0])
+            ix.search_raw(nq, q.data_ptr(), k, hd[ln].data_ptr(), hi[ln].data_ptr(), sp=sp)  # H2D + search + D2H, synchronous
+            return float(hd[ln][0, 0])
+        st = streams[ln]
+        with torch.cuda.stream(st):
+            qd = q.to(dev, non_blocking=True)
+            ix.search_device(nq, qd.data_ptr(), k, out_d[ln].data_ptr(), out_i[ln].data_ptr(), stream=st.cuda_stream, sp=sp)
+            dist.all_gather_into_tensor(g_d[ln].view(-1), out_d[ln].view(-1))
+            dist.all_gather_into_tensor(g_i[ln].view(-1), out_i[ln].view(-1))
+            b200vs.merge_topk_device(local_rank, world, nq, k, g_d[ln].data_ptr(), g_i[ln].data_ptr(), m_d[ln].data_ptr(), m_i[ln].data_ptr(), st.cuda_stream)
+            hd[ln].copy_(m_d[ln], non_blocking=True)
+            hi[ln].copy_(m_i[ln], non_blocking=True)
+        st.synchronize()
+        return float(hd[ln][0, 0])
 
-    for i in range(max(3, args.warmup)):
-        step_e2e(i)
+    def run_e2e(steps):
+        if world > 1 or L == 1:  # collectives stay on one caller thread
+            for i in range(steps):
+                step_e2e(i, 0)
+            return
+        def worker(t):
+            for i in range(t, steps, L):
+                step_e2e(i, t)
+        ths = [threading.Thread(target=worker, args=(t,)) for t in range(L)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+
+    run_e2e(max(3, args.warmup))
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_e2e(i)
+    run_e2e(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, e2e_s * 1e3, ms_single], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = t.tolist()
+        ms, e2e_ms, ms_single = t.tolist()
     else:
         e2e_ms = e2e_s * 1e3
     qps = nq * args.steps / (ms / 1e3)
@@ -342,7 +377,7 @@ def main():
     ix.set_profiling(True)
     kt, rows = [], 0
     for i in range(3):
-        ix.search_device(nq, q_dev[i % nbatches].data_ptr(), k, out_d.data_ptr(), out_i.data_ptr(), stream=stream.cuda_stream, sp=sp)
+        ix.search_device(nq, q_dev[i % nbatches].data_ptr(), k, out_d[0].data_ptr(), out_i[0].data_ptr(), stream=stream.cuda_stream, sp=sp)
         torch.cuda.synchronize()
         st = ix.stats()
         kt.append(st[3] / 1e9)
@@ -374,8 +409,8 @@ def main():
         t = time.time()
         Do, Io = o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq[:sample], k, args.nprobe, nthreads=cores)
         cpu_s = time.time() - t
-        ix.search_raw(nq, q_host[0].data_ptr(), k, hd.data_ptr(), hi.data_ptr(), sp=sp)
-        Ig, Dg = hi.numpy()[:sample], hd.numpy()[:sample]
+        ix.search_raw(nq, q_host[0].data_ptr(), k, hd[0].data_ptr(), hi[0].data_ptr(), sp=sp)
+        Ig, Dg = hi[0].numpy()[:sample], hd[0].numpy()[:sample]
         recall_vs_oracle = float(np.mean([len(set(a) & set(b)) / k for a, b in zip(Ig, Io)]))
         ids_exact = bool(np.array_equal(Ig, Io))
         cpu_baseline = {"value": sample / cpu_s, "unit": "queries/s", "cores": cores, "kind": "port",
@@ -390,6 +425,8 @@ def main():
                 "config": workload_config(args, world),
                 "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 12,
                         "ms_per_step": e2e_ms / args.steps},
+                "single_stream": {"value": nq * args.steps / (ms_single / 1e3), "unit": "queries/s", "ms_per_step": ms_single / args.steps,
+                                  "note": "same K steps strictly back to back on one stream"},
                 "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "recall_at_10_vs_oracle": recall_vs_oracle, "build_seconds": build_s, "search_stats": ix.stats()}
         print(json.dumps(line), flush=True)

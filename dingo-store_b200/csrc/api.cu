@@ -158,11 +158,9 @@ int b200vs_search_device(b200vs_index* h, int64_t nq, const float* xq_dev, int32
     if (k <= 0) return B200VS_OK;  // "topk <= 0 -> OK", flat.cc:212
     if (!out_ids_dev) fail(B200VS_EILLEGAL_PARAMETERS, "null output");
     std::shared_lock<std::shared_mutex> rl(ix->rw);
-    std::lock_guard<std::mutex> gl(ix->gpu_mu);
     ix->set_device();
-    cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
-    if (s != ix->last_stream) { B200VS_CUDA(cudaStreamSynchronize(ix->last_stream)); ix->last_stream = s; }
-    ix->scratch.reset(s);
+    LaneGuard lane(ix, (cudaStream_t)stream);
+    cudaStream_t s = lane.stream;
     for (int i = 0; i < 8; ++i) ix->stats[i] = 0;
     SearchCtx sc = make_ctx(ix, sp, s);
     ix->search_dev(nq, xq_dev, k, sc, out_dist_dev, (long long*)out_ids_dev, s);
@@ -178,11 +176,9 @@ int b200vs_search(b200vs_index* h, int64_t nq, const float* xq, int32_t k, const
     if (k <= 0) return B200VS_OK;
     if (!out_ids || !out_dist) fail(B200VS_EILLEGAL_PARAMETERS, "null output");
     std::shared_lock<std::shared_mutex> rl(ix->rw);
-    std::lock_guard<std::mutex> gl(ix->gpu_mu);
     ix->set_device();
-    cudaStream_t s = ix->stream;
-    if (s != ix->last_stream) { B200VS_CUDA(cudaStreamSynchronize(ix->last_stream)); ix->last_stream = s; }
-    ix->scratch.reset(s);
+    LaneGuard lane(ix, nullptr);  // host-pointer call: a free lane on its own stream, so concurrent callers overlap
+    cudaStream_t s = lane.stream;
     for (int i = 0; i < 8; ++i) ix->stats[i] = 0;
     float* dq = ix->scratch.alloc<float>((size_t)nq * ix->dim);
     float* dd = ix->scratch.alloc<float>((size_t)nq * k);
@@ -205,11 +201,9 @@ int b200vs_range_search(b200vs_index* h, int64_t nq, const float* xq, float radi
     if (ix->type == B200VS_HNSW) fail(B200VS_EVECTOR_NOT_SUPPORT, "RangeSearch not support in Hnsw!!!");  // hnsw.cc:487-493
     if (max_results <= 0 || !out_ids || !out_dist || !out_counts) fail(B200VS_EILLEGAL_PARAMETERS, "bad range-search outputs");
     std::shared_lock<std::shared_mutex> rl(ix->rw);
-    std::lock_guard<std::mutex> gl(ix->gpu_mu);
     ix->set_device();
-    cudaStream_t s = ix->stream;
-    if (s != ix->last_stream) { B200VS_CUDA(cudaStreamSynchronize(ix->last_stream)); ix->last_stream = s; }
-    ix->scratch.reset(s);
+    LaneGuard lane(ix, nullptr);
+    cudaStream_t s = lane.stream;
     float* dq = ix->scratch.alloc<float>((size_t)nq * ix->dim);
     float* dd = ix->scratch.alloc<float>((size_t)nq * max_results);
     long long* di = ix->scratch.alloc<long long>((size_t)nq * max_results);

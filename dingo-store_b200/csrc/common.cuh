@@ -99,7 +99,7 @@ __device__ __forceinline__ float quad_distance(const float* __restrict__ x, cons
   const int nfull = d >> 4;
   const float* xp = x + 4 * t;
   const float* qp = q + 4 * t;
-#pragma unroll 8
+#pragma unroll 16
   for (int c = 0; c < nfull; ++c) {
     const float4 xv = ld_f4(xp, vec);
     const float4 qv = ld_f4(qp, vec);

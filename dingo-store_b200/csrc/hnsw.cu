@@ -488,8 +488,11 @@ struct HnswIndex : IndexBase {
     return r;
   }
 
-  void upload(cudaStream_t s) {  // called with gpu_mu held (from search)
+  std::mutex upload_mu;
+  void upload(cudaStream_t s) {  // searches on different lanes may race to refresh the device mirror
+    std::lock_guard<std::mutex> ul(upload_mu);
     if (!dirty) return;
+    quiesce();  // earlier searches may still be reading the buffers this refresh reallocates
     const int64_t n = G.n;
     if (n == 0) { dirty = false; return; }
     d_data.reserve((size_t)std::max<int64_t>(n, (int64_t)(d_data.cap / dim)) * dim, (size_t)uploaded_rows * dim, s);

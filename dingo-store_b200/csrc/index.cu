@@ -12,6 +12,31 @@
 namespace b200vs {
 
 thread_local std::string g_last_error;
+thread_local Lane* IndexBase::tl_lane = nullptr;
+thread_local IndexBase* IndexBase::tl_owner = nullptr;
+
+LaneGuard::LaneGuard(IndexBase* ix_, cudaStream_t s) : ix(ix_), lane(nullptr), prev_owner(IndexBase::tl_owner), prev_lane(IndexBase::tl_lane), stream(s) {
+  if (s) {  // caller-provided stream: reuse the lane that last ran on it, else take the next one round-robin
+    for (int i = 0; i < kLanes && !lane; ++i) if (ix->lanes[i].last == s) lane = &ix->lanes[i];
+    if (!lane) lane = &ix->lanes[ix->lane_rr.fetch_add(1) % kLanes];
+    lane->mu.lock();
+  } else {  // host-pointer call: first free lane, on that lane's own stream
+    for (int i = 0; i < kLanes && !lane; ++i) if (ix->lanes[i].mu.try_lock()) lane = &ix->lanes[i];
+    if (!lane) { lane = &ix->lanes[ix->lane_rr.fetch_add(1) % kLanes]; lane->mu.lock(); }
+    if (!lane->own) B200VS_CUDA(cudaStreamCreateWithFlags(&lane->own, cudaStreamNonBlocking));
+    stream = lane->own;
+  }
+  if (lane->last && lane->last != stream) cudaStreamSynchronize(lane->last);
+  lane->last = stream;
+  IndexBase::tl_owner = ix;
+  IndexBase::tl_lane = lane;
+  lane->s.reset(stream);
+}
+LaneGuard::~LaneGuard() {
+  IndexBase::tl_owner = prev_owner;
+  IndexBase::tl_lane = prev_lane;
+  lane->mu.unlock();
+}
 
 IndexBase::IndexBase(b200vs_type t, b200vs_metric m, int d, const b200vs_params& p)
     : type(t), metric(m), dim(d), device(p.device), params(p) {
@@ -22,6 +47,7 @@ IndexBase::IndexBase(b200vs_type t, b200vs_metric m, int d, const b200vs_params&
 IndexBase::~IndexBase() {
   cudaSetDevice(device);
   if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+  for (auto& l : lanes) if (l.own) { cudaStreamSynchronize(l.own); cudaStreamDestroy(l.own); }
 }
 
 const float* IndexBase::prepare_queries(int64_t nq, const float* xq_dev, cudaStream_t s) {
@@ -135,6 +161,7 @@ struct FlatIndex : IndexBase {
     std::unique_lock<std::shared_mutex> wl(rw);
     std::lock_guard<std::mutex> gl(gpu_mu);
     set_device();
+    quiesce();
     scratch.reset(stream);
     std::vector<int64_t> dead;
     for (int64_t i = 0; i < n; ++i) {
@@ -169,6 +196,7 @@ struct FlatIndex : IndexBase {
     std::unique_lock<std::shared_mutex> wl(rw);
     std::lock_guard<std::mutex> gl(gpu_mu);
     set_device();
+    quiesce();
     scratch.reset(stream);
     std::vector<int64_t> dead;
     for (int64_t i = 0; i < n; ++i) {
@@ -277,6 +305,7 @@ struct IvfFlatIndex : IndexBase {
   bool is_trained() const override { return trained; }
 
   void install_centroids(const float* host_c, int k) {
+    quiesce();
     nlist = k;
     centroids.free(); cent_ids.free(); cent_norms.free();
     centroids.reserve((size_t)k * dim, 0, stream);
@@ -330,9 +359,9 @@ struct IvfFlatIndex : IndexBase {
     const int64_t chunk = 32768;
     for (int64_t a = 0; a < n; a += chunk) {
       const int64_t m = std::min(chunk, n - a);
-      const size_t mark = scratch.used;
+      const size_t mark = scratch.mark();
       run_scan(this, j, m, x_dev + (size_t)a * dim, 1, nullptr, nullptr, out_list_dev + a, nullptr, s);
-      scratch.used = mark;  // stream-ordered reuse
+      scratch.release(mark);  // stream-ordered reuse
     }
   }
 
@@ -390,6 +419,7 @@ void IvfFlatIndex::train(int64_t n, const float* x) {
   std::lock_guard<std::mutex> gl(gpu_mu);
   if (trained) return;  // ivf_flat.cc:670-672
   set_device();
+  quiesce();
   scratch.reset(stream);
   int k = nlist;
   if (n < k) k = 1;  // "data size too small, nlist degenerate to 1", ivf_flat.cc:676-680
@@ -402,9 +432,9 @@ void IvfFlatIndex::train(int64_t n, const float* x) {
     const int64_t chunk = 32768;
     for (int64_t a = 0; a < m; a += chunk) {
       const int64_t mm = std::min(chunk, m - a);
-      const size_t mark = scratch.used;
+      const size_t mark = scratch.mark();
       run_scan(this, j, mm, xd + (size_t)a * dim, 1, nullptr, nullptr, out + a, nullptr, stream);
-      scratch.used = mark;
+      scratch.release(mark);
     }
   }, [&](int kk) { cent_ids.free(); cent_ids.reserve(kk, 0, stream); launch_iota(cent_ids.p, kk, stream); });
   install_centroids(cent.data(), k);
@@ -415,6 +445,7 @@ void IvfFlatIndex::add(int64_t n, const float* x, const int64_t* in_ids, bool up
   if (!trained) fail(B200VS_EVECTOR_NOT_TRAIN, "not train");  // ivf_flat.cc:111-113 (caller trains and retries, :136-150)
   std::lock_guard<std::mutex> gl(gpu_mu);
   set_device();
+  quiesce();
   scratch.reset(stream);
   if (upsert) remove_locked(n, in_ids);  // ivf_flat.cc:115-118
   float* st = scratch.alloc<float>((size_t)n * dim);
@@ -492,6 +523,7 @@ int64_t IvfFlatIndex::remove(int64_t n, const int64_t* del) {
   if (!trained) return -1;  // signalled as OK by the ABI
   std::lock_guard<std::mutex> gl(gpu_mu);
   set_device();
+  quiesce();
   scratch.reset(stream);
   const int64_t r = remove_locked(n, del);
   maybe_compact();

@@ -78,6 +78,17 @@ struct Scratch {
   }
 };
 
+// A lane = one in-flight search: its own scratch arena, serialised by its own mutex, stream-ordered.  Several lanes let
+// concurrent callers (the reference issues searches from a 16-thread pool, src/server/server.cc:868-873) overlap on the
+// GPU: the small kernels of one batch run under the HBM-bound list scan of another.
+struct Lane {
+  Scratch s;
+  std::mutex mu;
+  cudaStream_t last = nullptr;  // stream of the lane's previous search (switching streams synchronises the old one)
+  cudaStream_t own = nullptr;   // lane-owned stream for host-pointer calls
+};
+constexpr int kLanes = 4;
+
 struct SearchCtx {  // resolved per-search parameters, device filter included
   int nprobe = 0;
   int efsearch = 0;
@@ -98,8 +109,22 @@ struct IndexBase {
   cudaStream_t stream = nullptr;
   cudaStream_t last_stream = nullptr;
   std::shared_mutex rw;  // readers = searches, writers = add/remove/train (reference RWLock)
-  std::mutex gpu_mu;     // serialises scratch + stream use between concurrent readers
-  Scratch scratch;
+  std::mutex gpu_mu;     // writers / maintenance (they also hold rw exclusively)
+  Lane lanes[kLanes];
+  std::atomic<unsigned> lane_rr{0};
+  static thread_local Lane* tl_lane;       // the calling thread's active lane (set by LaneGuard)
+  static thread_local IndexBase* tl_owner;
+  Lane& cur() { return (tl_owner == this && tl_lane) ? *tl_lane : lanes[0]; }
+  // wait for the asynchronous work of every earlier search (device-pointer searches return before the GPU is done);
+  // writers call it before touching index memory or the lane-0 scratch
+  void quiesce() { for (auto& l : lanes) if (l.last) cudaStreamSynchronize(l.last); }
+  struct ScratchProxy {  // `ix->scratch.alloc<T>(n)` resolves to the calling thread's lane
+    IndexBase* ix;
+    template <class T> T* alloc(size_t n) { return ix->cur().s.alloc<T>(n); }
+    void reset(cudaStream_t st) { ix->cur().s.reset(st); }
+    size_t mark() { return ix->cur().s.used; }
+    void release(size_t m) { ix->cur().s.used = m; }
+  } scratch{this};
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool profiling = false;  // b200vs_set_profiling: time the dominant scan kernel with CUDA events
 
@@ -132,6 +157,17 @@ struct IndexBase {
   // helpers shared by the index types
   const float* prepare_queries(int64_t nq, const float* xq_dev, cudaStream_t s);  // cosine -> normalised copy
   void launch_count(int n = 1) { stats[0] += n; }
+};
+
+// RAII: pick a lane for a search on stream `s` (nullptr = a lane-owned stream), lock it, make it the thread's scratch
+struct LaneGuard {
+  IndexBase* ix;
+  Lane* lane;
+  IndexBase* prev_owner;
+  Lane* prev_lane;
+  cudaStream_t stream;
+  LaneGuard(IndexBase* ix_, cudaStream_t s);
+  ~LaneGuard();
 };
 
 IndexBase* make_flat(b200vs_metric m, int d, const b200vs_params& p);

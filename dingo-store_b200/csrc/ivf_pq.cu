@@ -211,6 +211,7 @@ struct IvfPqIndex : IndexBase {
   bool is_trained() const override { return mode != kNone; }
 
   void install(const float* h_cent, const float* h_cb) {
+    quiesce();
     centroids.free(); codebooks.free(); pre.free(); cent_ids.free();
     centroids.reserve((size_t)nlist * dim, 0, stream);
     codebooks.reserve((size_t)M * KSUB * (dim / M), 0, stream);
@@ -263,9 +264,9 @@ struct IvfPqIndex : IndexBase {
     const int64_t chunk = 32768;
     for (int64_t a = 0; a < n; a += chunk) {
       const int64_t m = std::min(chunk, n - a);
-      const size_t mark = scratch.used;
+      const size_t mark = scratch.mark();
       run_scan(this, j, m, x_dev + (size_t)a * dd, 1, nullptr, nullptr, out + a, nullptr, stream);
-      scratch.used = mark;
+      scratch.release(mark);
     }
   }
 
@@ -285,6 +286,7 @@ struct IvfPqIndex : IndexBase {
     std::unique_lock<std::shared_mutex> wl(rw);
     std::lock_guard<std::mutex> gl(gpu_mu);
     set_device();
+    quiesce();
     scratch.reset(stream);
     const bool l2 = metric == B200VS_L2;
     DevBuf<long long> cid;
@@ -339,6 +341,7 @@ struct IvfPqIndex : IndexBase {
     if (mode == kNone) fail(B200VS_EVECTOR_NOT_TRAIN, "not train");
     std::lock_guard<std::mutex> gl(gpu_mu);
     set_device();
+    quiesce();
     scratch.reset(stream);
     if (upsert) remove_locked(n, in_ids);
     float* st = scratch.alloc<float>((size_t)n * dim);
@@ -411,6 +414,7 @@ struct IvfPqIndex : IndexBase {
     if (mode == kNone) return -1;
     std::lock_guard<std::mutex> gl(gpu_mu);
     set_device();
+    quiesce();
     scratch.reset(stream);
     const int64_t r = remove_locked(n, del);
     maybe_compact();
@@ -421,9 +425,10 @@ struct IvfPqIndex : IndexBase {
     if (mode == kNone) { fill_empty_results(nq, k, od, oi, s); return; }  // ivf_pq.cc:159-163
     if (mode == kFlat) {  // delegate to the inner Flat index, sharing this call's stream and scratch discipline
       std::shared_lock<std::shared_mutex> rl(flat->rw);
-      std::lock_guard<std::mutex> gl(flat->gpu_mu);
-      flat->scratch.reset(s);
+      LaneGuard lg(flat.get(), s);
       SearchCtx sc2 = sc;
+      if (sc.sorted_ids_dev) {  // the filter list lives in the outer lane's scratch: still valid (same stream, still locked)
+      }
       flat->search_dev(nq, xq, k, sc2, od, oi, s);
       for (int i = 0; i < 8; ++i) stats[i] = flat->stats[i];
       return;
@@ -477,8 +482,7 @@ struct IvfPqIndex : IndexBase {
                         int* oc, cudaStream_t s) override {
     if (mode == kFlat) {
       std::shared_lock<std::shared_mutex> rl(flat->rw);
-      std::lock_guard<std::mutex> gl(flat->gpu_mu);
-      flat->scratch.reset(s);
+      LaneGuard lg(flat.get(), s);
       flat->range_search_dev(nq, xq, radius, max_results, sc, od, oi, oc, s);
       return;
     }

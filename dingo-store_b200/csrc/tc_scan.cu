@@ -550,6 +550,14 @@ __device__ int window_select(unsigned long long* keys, int n, int k, float two_e
   *a_k_out = a_k;
   const int quad = threadIdx.x >> 2, t = threadIdx.x & 3;
   const bool vec = (d & 3) == 0;
+  {  // pull every in-window row into L2 at once (random 3 KB gathers: latency-bound otherwise)
+    const int lines = (d * 4 + 127) / 128;
+    for (int i = threadIdx.x; i < m * lines; i += blockDim.x) {
+      const long long row = (long long)(uint32_t)(keys[i / lines] & 0xffffffffull);
+      const char* ptr = reinterpret_cast<const char*>(vecs + (size_t)row * d) + (size_t)(i % lines) * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    }
+  }
   for (int base = 0; base < m; base += SCAN_QUADS) {
     const int i = base + quad;
     const bool valid = i < m;
@@ -612,23 +620,23 @@ tc_final_fast_kernel(const unsigned long long* __restrict__ cand, const int* __r
 template <bool L2>
 static __global__ void __launch_bounds__(SCAN_THREADS)
 tc_coarse_final_fast_kernel(const float* __restrict__ dense, long long ld, int nrows, const float* __restrict__ qnorm, float max_norm,
-                            const float* __restrict__ q, const float* __restrict__ vecs, int d, int k, long long* out_probes,
-                            float* out_raw) {
+                            const float* __restrict__ q, const float* __restrict__ vecs, int d, int k, int maxw,
+                            long long* out_probes, float* out_raw) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_m;
   const int qi = blockIdx.x;
   float* qs = reinterpret_cast<float*>(smem);
   const size_t qbytes = ((size_t)d * 4 + 15) / 16 * 16;
-  long long* ex_id = reinterpret_cast<long long*>(smem + qbytes);                              // [COARSE_FAST]
-  uint32_t* ex_kd = reinterpret_cast<uint32_t*>(smem + qbytes + (size_t)COARSE_FAST * 8);      // [COARSE_FAST]
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + qbytes + (size_t)COARSE_FAST * 12);  // [COARSE_FAST]
+  long long* ex_id = reinterpret_cast<long long*>(smem + qbytes);                       // [maxw]   maxw = pow2(nrows)
+  uint32_t* ex_kd = reinterpret_cast<uint32_t*>(smem + qbytes + (size_t)maxw * 8);      // [maxw]
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + qbytes + (size_t)maxw * 12);  // [maxw]
   for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = q[(size_t)qi * d + i];
   for (int i = threadIdx.x; i < nrows; i += blockDim.x) keys[i] = ((unsigned long long)f2ord(dense[(size_t)qi * ld + i]) << 32) | (unsigned)i;
   __syncthreads();
   bool fits;
   float a_k;
   const float two_eps = 2.f * tc_eps(L2, qnorm[qi], max_norm, d, true);
-  const int have = window_select<L2, true>(keys, nrows, k, two_eps, qs, vecs, nullptr, d, ex_kd, ex_id, COARSE_FAST, &fits, &a_k, &s_m);
+  const int have = window_select<L2, true>(keys, nrows, k, two_eps, qs, vecs, nullptr, d, ex_kd, ex_id, maxw, &fits, &a_k, &s_m);
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     out_probes[(size_t)qi * k + i] = i < have ? ex_id[i] : -1;
     if (out_raw) { const float v = i < have ? ord2f(ex_kd[i]) : 0.f; out_raw[(size_t)qi * k + i] = L2 ? v : -v; }
@@ -909,7 +917,7 @@ struct TcPlan {
 static TcPlan tc_prepare(IndexBase* ix, const TcView& v, int64_t nq, const float* q, const long long* probes, int nprobe, cudaStream_t s) {
   tc_init(ix->device);
   const int d = ix->dim;
-  Scratch& S = ix->scratch;
+  auto& S = ix->scratch;
   TcPlan P;
   P.npairs = nq * nprobe;
   P.bound = tc_item_bound(v, P.npairs);
@@ -964,7 +972,7 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
                int nprobe, const SearchCtx& sc, float* out_dist, long long* out_ids, cudaStream_t s) {
   const int d = ix->dim;
   const int cap = tc_cand_cap(k);
-  Scratch& S = ix->scratch;
+  auto& S = ix->scratch;
   TcPlan P = tc_prepare(ix, v, nq, q, probes, nprobe, s);
   float* sample = S.alloc<float>((size_t)P.sbound * TC_NQT * TC_SAMPLE);
   float* tau = S.alloc<float>(nq);
@@ -1036,7 +1044,7 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   tc_init(ix->device);
   const int d = ix->dim;
   const int nrows = (int)v.arena_rows;
-  Scratch& S = ix->scratch;
+  auto& S = ix->scratch;
   float* qhi = S.alloc<float>((size_t)nq * d);
   float* qlo = S.alloc<float>((size_t)nq * d);
   float* qnorm = S.alloc<float>(nq);
@@ -1062,9 +1070,10 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(a_hi, a_hi, b16, b32, b64, a_lo, l16, l32, l64, p);
   B200VS_CUDA(cudaGetLastError());
   if (nrows <= COARSE_FAST && nprobe <= nrows) {
-    const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)COARSE_FAST * 20;
-    if (l2) tc_coarse_final_fast_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, out_probes, out_raw);
-    else tc_coarse_final_fast_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, out_probes, out_raw);
+    const int maxw = std::max(2, next_pow2(nrows));
+    const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)maxw * 20;
+    if (l2) tc_coarse_final_fast_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, out_probes, out_raw);
+    else tc_coarse_final_fast_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, out_probes, out_raw);
   } else {
     const int pool = select_pool_cap(nprobe, SCAN_THREADS);
     const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + BlockSelect::smem_bytes(pool);
