@@ -250,7 +250,7 @@ def main():
     gq.manual_seed(4321)
     nbatches = 4
     q_dev = [torch.rand((nq, d), generator=gq, device=dev, dtype=torch.float32) for _ in range(nbatches)]
-    L = max(1, args.in_flight)
+    L = max(1, args.in_flight) if world == 1 else 1  # multi-GPU: the collectives of a process group stay on one stream
     out_d = [torch.empty((nq, k), dtype=torch.float32, device=dev) for _ in range(L)]
     out_i = [torch.empty((nq, k), dtype=torch.int64, device=dev) for _ in range(L)]
     sp, _keep = b200vs.make_search_params(nprobe=args.nprobe, exact_only=args.exact_only)

@@ -1,0 +1,234 @@
+#!/usr/bin/env python
+"""bench_configs.py — the OTHER BASELINE.json configs (bench.py measures the headline one), one JSON line each.
+
+  cfg1  Flat L2, 100K x 128, top-10, batch = 1            (the reference's own CPU-runnable case)
+  cfg2  IVF-Flat L2, 1M x 768, nlist 1024, nprobe 32, batch 256, top-10
+  cfg3  IVF-PQ IP, N x 768, M = 96, nbits 8, nlist 2048, nprobe 64, batch 1024, top-100   (N scaled, see --pq-n)
+  cfg4  HNSW cosine, N x 768, M = 16, efConstruction 200, efSearch 128, batch 512          (N scaled: host build)
+Each line: device-resident QPS (CUDA events), e2e QPS through the host-pointer C ABI, parity with the oracle on a
+bounded sample, the dominant kernel's time from the library's profiling mode and the algorithmic figure of
+SURVEY.md §8(d).  Scaled sizes are stated in the line ("scaled_from").  Not part of the driver contract.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "dingo-store_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+import b200vs  # noqa: E402
+import oracle_lib  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def time_search(ix, xq, k, steps=20, warmup=5, **kw):
+    dev = torch.device("cuda", 0)
+    nq = xq.shape[0]
+    q = torch.from_numpy(xq).to(dev)
+    od = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    oi = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    sp, keep = b200vs.make_search_params(**kw)
+    st = torch.cuda.Stream(device=dev)
+    for _ in range(warmup):
+        ix.search_device(nq, q.data_ptr(), k, od.data_ptr(), oi.data_ptr(), stream=st.cuda_stream, sp=sp)
+    st.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(steps):
+        ix.search_device(nq, q.data_ptr(), k, od.data_ptr(), oi.data_ptr(), stream=st.cuda_stream, sp=sp)
+    e1.record(st)
+    st.synchronize()
+    dev_ms = e0.elapsed_time(e1) / steps
+    qh = torch.from_numpy(xq).pin_memory()
+    hd = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    hi = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    for _ in range(warmup):
+        ix.search_raw(nq, qh.data_ptr(), k, hd.data_ptr(), hi.data_ptr(), sp=sp)
+    t = time.perf_counter()
+    for _ in range(steps):
+        ix.search_raw(nq, qh.data_ptr(), k, hd.data_ptr(), hi.data_ptr(), sp=sp)
+    e2e_ms = (time.perf_counter() - t) / steps * 1e3
+    ix.set_profiling(True)
+    ix.search_device(nq, q.data_ptr(), k, od.data_ptr(), oi.data_ptr(), stream=st.cuda_stream, sp=sp)
+    st.synchronize()
+    stats = ix.stats()
+    ix.set_profiling(False)
+    return dev_ms, e2e_ms, stats, hd.numpy().copy(), hi.numpy().copy()
+
+
+def rnd(n, d, seed, dist="uniform"):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    out = np.empty((n, d), np.float32)
+    for a in range(0, n, 262144):
+        m = min(262144, n - a)
+        x = torch.rand((m, d), generator=g, device="cuda") if dist == "uniform" else torch.randn((m, d), generator=g, device="cuda")
+        out[a:a + m] = x.cpu().numpy()
+    return out
+
+
+def cfg1(o, cores):
+    n, d, k = 100_000, 128, 10
+    xb = rnd(n, d, 1234)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    ix = b200vs.Index(b200vs.FLAT, b200vs.L2, d)
+    for a in range(0, n, 32768):
+        ix.add(xb[a:a + 32768], ids[a:a + 32768])
+    xq = rnd(1, d, 4321)
+    dev_ms, e2e_ms, st, D, I = time_search(ix, xq, k, steps=200, warmup=20)
+    t = time.perf_counter()
+    reps = 20
+    for _ in range(reps):
+        Do, Io = o.flat_search(oracle_lib.L2, xb, ids, xq, k, nthreads=1)
+    cpu_ms = (time.perf_counter() - t) / reps * 1e3
+    bytes_q = n * d * 4
+    return {"config": "cfg1 Flat L2 100Kx128 top-10 batch=1", "qps_device": 1e3 / dev_ms, "latency_ms_device": dev_ms, "qps_e2e": 1e3 / e2e_ms,
+            "ids_bit_exact": bool(np.array_equal(I, Io)), "dist_bit_exact": bool(np.array_equal(D.view(np.uint32), Do.view(np.uint32))),
+            "algorithmic_bytes_per_query": bytes_q, "achieved_gbs_whole_call": bytes_q / (dev_ms * 1e-3) / 1e9, "hbm_peak_gbs": peak(),
+            "cpu_baseline": {"qps": 1e3 / cpu_ms, "cores": 1, "kind": "port", "sample": "the same single query, one thread (the reference runs one query per task)"},
+            "path": "exact FP32 scan (batch < 16)", "search_stats": st}
+
+
+def cfg2(o, cores):
+    n, d, nlist, nprobe, nq, k = 1_000_000, 768, 1024, 32, 256, 10
+    xb = rnd(n, d, 1234)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    ix = b200vs.Index(b200vs.IVF_FLAT, b200vs.L2, d, nlist=nlist)
+    ix.train(xb[:nlist * 256])
+    for a in range(0, n, 32768):
+        ix.add(xb[a:a + 32768], ids[a:a + 32768])
+    xq = rnd(nq, d, 4321)
+    dev_ms, e2e_ms, st, D, I = time_search(ix, xq, k, nprobe=nprobe)
+    off, lx, _, lids = ix.export_lists(nlist)
+    lx = o.numa_spread(lx, cores)
+    cent = ix.get_trained_state()[32:].view(np.float32).reshape(nlist, d)
+    t = time.perf_counter()
+    Do, Io = o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq, k, nprobe, nthreads=cores)
+    cpu_s = time.perf_counter() - t
+    rows = st[4]
+    return {"config": "cfg2 IVF-Flat L2 1Mx768 nlist=1024 nprobe=32 batch=256 top-10", "qps_device": nq / dev_ms * 1e3, "ms_per_batch_device": dev_ms,
+            "qps_e2e": nq / e2e_ms * 1e3, "ids_bit_exact": bool(np.array_equal(I, Io)), "dist_bit_exact": bool(np.array_equal(D.view(np.uint32), Do.view(np.uint32))),
+            "recall_at_10_vs_oracle": float(np.mean([len(set(a) & set(b)) / k for a, b in zip(I, Io)])),
+            "roofline": {"bound": "hbm", "kernel": "tc_scan_kernel capture pass", "kernel_ms": st[3] / 1e6, "algorithmic_bytes": rows * (d * 4 + 8),
+                         "achieved": rows * (d * 4 + 8) / max(st[3], 1) , "unit": "GB/s", "peak": peak(), "frac": rows * (d * 4 + 8) / max(st[3], 1) / peak()},
+            "cpu_baseline": {"qps": nq / cpu_s, "cores": cores, "kind": "port", "sample": f"all {nq} queries, {cores} threads, one query per task"},
+            "fallback_queries": st[2], "search_stats": st}
+
+
+def cfg3(o, cores, n):
+    d, M, nlist, nprobe, nq, k = 768, 96, 2048, 64, 1024, 100
+    ix = b200vs.Index(b200vs.IVF_PQ, b200vs.IP, d, nlist=nlist, pq_m=M, pq_nbits=8)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1234)
+    t0 = time.time()
+    ntrain = max(256 * nlist, 65536)
+    train = torch.randn((ntrain, d), generator=g, device="cuda").cpu().numpy()
+    ix.train(train)
+    t_train = time.time() - t0
+    keep = None
+    t0 = time.time()
+    nid = 1
+    for a in range(0, n, 131072):
+        m = min(131072, n - a)
+        x = torch.randn((m, d), generator=g, device="cuda").cpu().numpy()
+        if keep is None:
+            keep = x[:20000].copy()
+        for b in range(0, m, 32768):
+            mm = min(32768, m - b)
+            ix.add(x[b:b + mm], np.arange(nid, nid + mm, dtype=np.int64))
+            nid += mm
+    t_add = time.time() - t0
+    xq = rnd(nq, d, 4321, "normal")
+    dev_ms, e2e_ms, st, D, I = time_search(ix, xq, k, steps=5, warmup=2, nprobe=nprobe)
+    # parity on a sample: oracle LUT scan over the exported codes with the GPU-trained state
+    blob = ix.get_trained_state()
+    cent = blob[48:48 + nlist * d * 4].view(np.float32).reshape(nlist, d)
+    cb = blob[48 + nlist * d * 4:].view(np.float32).reshape(M, 256, d // M)
+    off, _, codes, lids = ix.export_lists(nlist, with_vectors=False, code_size=M)
+    ns = 32
+    t = time.perf_counter()
+    Do, Io = o.ivfpq_search(oracle_lib.IP, cent, cb, off, codes, lids, xq[:ns], k, nprobe, nthreads=cores)
+    cpu_s = time.perf_counter() - t
+    lookups = float(st[4]) * M * 0 + 0  # per-batch lookups need the per-query probe sizes: use avg list len
+    avg_len = n / nlist
+    lookups = nq * nprobe * avg_len * M
+    return {"config": f"cfg3 IVF-PQ IP {n}x768 M=96 nbits=8 nlist=2048 nprobe=64 batch=1024 top-100", "scaled_from": "10M x 768" if n < 10_000_000 else None,
+            "qps_device": nq / dev_ms * 1e3, "ms_per_batch_device": dev_ms, "qps_e2e": nq / e2e_ms * 1e3,
+            "ids_bit_exact_sample": bool(np.array_equal(I[:ns], Io)), "recall_at_100_vs_oracle": float(np.mean([len(set(a) & set(b)) / k for a, b in zip(I[:ns], Io)])),
+            "max_rel_dist_err": float(np.max(np.abs(D[:ns] - Do) / np.maximum(np.abs(Do), 1e-6))),
+            "roofline": {"bound": "shared-memory LUT", "kernel": "pq_scan_select_kernel", "kernel_ms": st[3] / 1e6, "lookups_per_batch": lookups,
+                         "achieved_lookups_per_s": lookups / max(st[3] * 1e-9, 1e-9), "bytes_scan_equiv_gbs": lookups / max(st[3], 1), "hbm_peak_gbs": peak()},
+            "cpu_baseline": {"qps": ns / cpu_s, "cores": cores, "kind": "port", "sample": f"first {ns} queries, {cores} threads"},
+            "train_seconds": t_train, "add_seconds": t_add, "search_stats": st}
+
+
+def cfg4(o, cores, n):
+    d, M, efc, ef, nq, k = 768, 16, 200, 128, 512, 10
+    xb = rnd(n, d, 1234)
+    labels = np.arange(1, n + 1, dtype=np.int64)
+    ix = b200vs.Index(b200vs.HNSW, b200vs.COSINE, d, hnsw_m=M, hnsw_efc=efc, max_elements=n * 2)
+    t0 = time.time()
+    for a in range(0, n, 8192):
+        ix.add(xb[a:a + 8192], labels[a:a + 8192])
+    t_build = time.time() - t0
+    xq = rnd(nq, d, 4321)
+    dev_ms, e2e_ms, st, D, I = time_search(ix, xq, k, steps=5, warmup=2, efsearch=ef)
+    # oracle on the SAME graph (loaded from the engine's export), sample of queries
+    h = oracle_lib.OracleHnsw(o, oracle_lib.COSINE, d, n, M, efc)
+    t0 = time.time()
+    h.add(xb, labels)
+    t_oracle_build = time.time() - t0
+    same_graph = bool(np.array_equal(ix.get_trained_state(), h.export()))
+    t = time.perf_counter()
+    Do, Io, nd, nh = h.search(xq, k, ef=ef, nthreads=cores)
+    cpu_s = time.perf_counter() - t
+    bytes_batch = float(nd.sum()) * d * 4 + float(nh.sum()) * (4 + 2 * M * 4)
+    return {"config": f"cfg4 HNSW cosine {n}x768 M=16 efC=200 efSearch=128 batch=512 top-10", "scaled_from": "1M x 768 (graph is built on the host, single writer)",
+            "qps_device": nq / dev_ms * 1e3, "ms_per_batch_device": dev_ms, "qps_e2e": nq / e2e_ms * 1e3, "graph_equals_oracle_graph": same_graph,
+            "ids_bit_exact": bool(np.array_equal(I, Io)), "dist_bit_exact": bool(np.array_equal(D.view(np.uint32), Do.view(np.uint32))),
+            "roofline": {"bound": "hbm random gathers", "kernel": "hnsw_search_kernel", "kernel_ms": st[3] / 1e6, "algorithmic_bytes": bytes_batch,
+                         "ndis_per_query": float(nd.mean()), "hops_per_query": float(nh.mean()), "achieved": bytes_batch / max(st[3], 1), "unit": "GB/s",
+                         "peak": peak(), "frac": bytes_batch / max(st[3], 1) / peak()},
+            "cpu_baseline": {"qps": nq / cpu_s, "cores": cores, "kind": "port", "sample": f"all {nq} queries, {cores} threads"},
+            "build_seconds_engine": t_build, "build_seconds_oracle": t_oracle_build, "search_stats": st}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,2,3,4")
+    ap.add_argument("--pq-n", type=int, default=2_000_000)
+    ap.add_argument("--hnsw-n", type=int, default=50_000)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    o = oracle_lib.load()
+    cores = os.cpu_count() or 1
+    fns = {"1": lambda: cfg1(o, cores), "2": lambda: cfg2(o, cores), "3": lambda: cfg3(o, cores, a.pq_n), "4": lambda: cfg4(o, cores, a.hnsw_n)}
+    for c in a.configs.split(","):
+        t0 = time.time()
+        try:
+            line = fns[c]()
+        except Exception as e:  # keep going: one line per config
+            line = {"config": f"cfg{c}", "error": repr(e)}
+        line["wall_seconds"] = time.time() - t0
+        s = json.dumps(line)
+        print(s, flush=True)
+        if a.out:
+            with open(a.out, "a") as f:
+                f.write(s + "\n")
+
+
+if __name__ == "__main__":
+    main()

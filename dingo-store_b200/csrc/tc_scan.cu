@@ -147,13 +147,13 @@ static __global__ void tc_plan_kernel(const int* __restrict__ cnt, const int* __
 
 // one warp per (query, probe): place the pair and copy the rounded query row
 static __global__ void tc_fill_pairs_kernel(const long long* __restrict__ probes, const int* __restrict__ pos,
-                                            const int* __restrict__ pair_off, long long n, int nprobe, int d,
-                                            const float* __restrict__ q32, int* pair_query, float* bws) {
+                                            const int* __restrict__ pair_off, const int* __restrict__ list_len, long long n,
+                                            int nprobe, int d, const float* __restrict__ q32, int* pair_query, float* bws) {
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n) return;
   const long long l = probes[w];
-  if (l < 0) return;
+  if (l < 0 || list_len[l] <= 0) return;  // empty list (e.g. owned by another shard): no work item will read this row
   const int p = pair_off[l] + pos[w];
   const int q = (int)(w / nprobe);
   if (lane == 0) pair_query[p] = q;
@@ -525,23 +525,65 @@ __device__ __forceinline__ void block_sort_pair(uint32_t* kd, long long* kid, in
 // unsorted, padded storage for the next power of two.  Sorts once, takes the k-th approximate score, re-scores the
 // in-window prefix exactly (reference order) and returns the exact top-k in (ex_kd, ex_id)[0..k).
 // Returns the number of exact entries kept (<= k) and whether the prefix fit in `maxw`.
+// k-th smallest (k >= 1, n >= k) of the 32-bit keys stored in the high halves of keys[0..n): 4-pass radix select with a
+// 256-bin shared histogram (no sorting network, ~10 barriers).  All threads call; returns the key to all threads.
+__device__ uint32_t block_kth_key(const unsigned long long* keys, int n, int k) {
+  __shared__ int s_hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_k;
+  if (threadIdx.x == 0) { s_prefix = 0; s_k = k; }
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t key = (uint32_t)(keys[i] >> 32);
+      if (pass == 0 || ((key ^ prefix) >> (shift + 8)) == 0) atomicAdd(&s_hist[(key >> shift) & 255], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // warp 0: locate the bin that holds the k-th element
+      const int lane = threadIdx.x;
+      int loc[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { loc[j] = s_hist[lane * 8 + j]; sum += loc[j]; }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      const int kk = s_k;
+      const int before = incl - sum;
+      if (before < kk && kk <= incl) {  // exactly one lane
+        int acc = before;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (acc < kk && kk <= acc + loc[j]) { s_prefix = prefix | ((uint32_t)(lane * 8 + j) << shift); s_k = kk - acc; }
+          acc += loc[j];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  return s_prefix;
+}
+
+// Window select shared by the list-scan finish and the coarse finish.  keys[0..n) = (ord(approx score) << 32 | row),
+// unsorted.  Finds the k-th approximate score (radix select), gathers every row whose score is within two_eps of it,
+// re-scores those rows exactly (reference order) and sorts the exact (key, id) pairs: ex_kd/ex_id[0..returned).
+// Returns the number of exact entries kept (<= k); *fits = the window fit in `maxw` rows.
 template <bool L2, bool ROW_IS_ID>
-__device__ int window_select(unsigned long long* keys, int n, int k, float two_eps, const float* qs, const float* __restrict__ vecs,
-                             const long long* __restrict__ ids, int d, uint32_t* ex_kd, long long* ex_id, int maxw, bool* fits,
+__device__ int window_select(const unsigned long long* keys, int n, int k, float two_eps, const float* qs, const float* __restrict__ vecs,
+                             const long long* __restrict__ ids, int d, uint32_t* ex_kd, long long* ex_id, int* rows, int maxw, bool* fits,
                              float* a_k_out, int* s_m) {
-  int m2 = 2;
-  while (m2 < n) m2 <<= 1;
-  for (int i = n + threadIdx.x; i < m2; i += blockDim.x) keys[i] = ~0ull;
-  __syncthreads();
-  block_sort_u64(keys, m2);
-  const float a_k = n >= k ? ord2f((uint32_t)(keys[k - 1] >> 32)) : TC_INF;
+  const float a_k = n >= k ? ord2f(block_kth_key(keys, n, k)) : TC_INF;
   const float window = a_k + two_eps;
   if (threadIdx.x == 0) *s_m = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {  // sorted: the in-window rows are a prefix
-    const bool in = ord2f((uint32_t)(keys[i] >> 32)) <= window;
-    const bool next_in = (i + 1 < n) && ord2f((uint32_t)(keys[i + 1] >> 32)) <= window;
-    if (in && !next_in) *s_m = i + 1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long e = keys[i];
+    if (ord2f((uint32_t)(e >> 32)) <= window) {
+      const int pos = atomicAdd(s_m, 1);
+      if (pos < maxw) rows[pos] = (int)(uint32_t)(e & 0xffffffffull);
+    }
   }
   __syncthreads();
   int m = *s_m;
@@ -553,15 +595,14 @@ __device__ int window_select(unsigned long long* keys, int n, int k, float two_e
   {  // pull every in-window row into L2 at once (random 3 KB gathers: latency-bound otherwise)
     const int lines = (d * 4 + 127) / 128;
     for (int i = threadIdx.x; i < m * lines; i += blockDim.x) {
-      const long long row = (long long)(uint32_t)(keys[i / lines] & 0xffffffffull);
-      const char* ptr = reinterpret_cast<const char*>(vecs + (size_t)row * d) + (size_t)(i % lines) * 128;
+      const char* ptr = reinterpret_cast<const char*>(vecs + (size_t)(uint32_t)rows[i / lines] * d) + (size_t)(i % lines) * 128;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
     }
   }
   for (int base = 0; base < m; base += SCAN_QUADS) {
     const int i = base + quad;
     const bool valid = i < m;
-    const long long row = (long long)(uint32_t)(keys[valid ? i : 0] & 0xffffffffull);
+    const long long row = (long long)(uint32_t)rows[valid ? i : 0];
     const float v = quad_distance<L2>(vecs + (size_t)row * d, qs, d, t, vec);
     if (valid && t == 0) { ex_kd[i] = f2ord(L2 ? v : -v); ex_id[i] = ROW_IS_ID ? row : ids[row]; }
   }
@@ -590,7 +631,8 @@ tc_final_fast_kernel(const unsigned long long* __restrict__ cand, const int* __r
   const size_t qbytes = ((size_t)d * 4 + 15) / 16 * 16;
   long long* ex_id = reinterpret_cast<long long*>(smem + qbytes);                    // [FIN_MAXW]
   uint32_t* ex_kd = reinterpret_cast<uint32_t*>(smem + qbytes + (size_t)FIN_MAXW * 8);  // [FIN_MAXW]
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + qbytes + (size_t)FIN_MAXW * 12);  // [pow2(cap)]
+  int* rows = reinterpret_cast<int*>(smem + qbytes + (size_t)FIN_MAXW * 12);            // [FIN_MAXW]
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + qbytes + (size_t)FIN_MAXW * 16);  // [cap]
   for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = q[(size_t)qi * d + i];
   const int total = cand_cnt[qi];
   const int n = min(total, cap);
@@ -599,7 +641,7 @@ tc_final_fast_kernel(const unsigned long long* __restrict__ cand, const int* __r
   bool fits;
   float a_k;
   const float two_eps = 2.f * tc_eps(L2, qnorm[qi], max_norm, d, false);
-  const int have = window_select<L2, false>(keys, n, k, two_eps, qs, vecs, ids, d, ex_kd, ex_id, FIN_MAXW, &fits, &a_k, &s_m);
+  const int have = window_select<L2, false>(keys, n, k, two_eps, qs, vecs, ids, d, ex_kd, ex_id, rows, FIN_MAXW, &fits, &a_k, &s_m);
   const float tq = tau[qi];
   const bool certified = fits && (total <= cap) && (tq == TC_INF || a_k + two_eps <= tq);
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
@@ -629,14 +671,15 @@ tc_coarse_final_fast_kernel(const float* __restrict__ dense, long long ld, int n
   const size_t qbytes = ((size_t)d * 4 + 15) / 16 * 16;
   long long* ex_id = reinterpret_cast<long long*>(smem + qbytes);                       // [maxw]   maxw = pow2(nrows)
   uint32_t* ex_kd = reinterpret_cast<uint32_t*>(smem + qbytes + (size_t)maxw * 8);      // [maxw]
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + qbytes + (size_t)maxw * 12);  // [maxw]
+  int* rows = reinterpret_cast<int*>(smem + qbytes + (size_t)maxw * 12);                // [maxw]
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem + qbytes + (size_t)maxw * 16);  // [maxw]
   for (int i = threadIdx.x; i < d; i += blockDim.x) qs[i] = q[(size_t)qi * d + i];
   for (int i = threadIdx.x; i < nrows; i += blockDim.x) keys[i] = ((unsigned long long)f2ord(dense[(size_t)qi * ld + i]) << 32) | (unsigned)i;
   __syncthreads();
   bool fits;
   float a_k;
   const float two_eps = 2.f * tc_eps(L2, qnorm[qi], max_norm, d, true);
-  const int have = window_select<L2, true>(keys, nrows, k, two_eps, qs, vecs, nullptr, d, ex_kd, ex_id, maxw, &fits, &a_k, &s_m);
+  const int have = window_select<L2, true>(keys, nrows, k, two_eps, qs, vecs, nullptr, d, ex_kd, ex_id, rows, maxw, &fits, &a_k, &s_m);
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     out_probes[(size_t)qi * k + i] = i < have ? ex_id[i] : -1;
     if (out_raw) { const float v = i < have ? ord2f(ex_kd[i]) : 0.f; out_raw[(size_t)qi * k + i] = L2 ? v : -v; }
@@ -939,7 +982,7 @@ static TcPlan tc_prepare(IndexBase* ix, const TcView& v, int64_t nq, const float
   tc_prep_queries_kernel<<<(unsigned)cdiv(nq * 32, 256), 256, 0, s>>>(q, nq, d, P.q32, P.qnorm);
   tc_count_pairs_kernel<<<(unsigned)cdiv(P.npairs, 256), 256, 0, s>>>(probes, P.npairs, P.cnt, P.pos);
   tc_plan_kernel<<<1, 1024, 0, s>>>(P.cnt, v.list_len, v.nlist, P.pair_off, P.item_off, P.totals);
-  tc_fill_pairs_kernel<<<(unsigned)cdiv(P.npairs * 32, 256), 256, 0, s>>>(probes, P.pos, P.pair_off, P.npairs, nprobe, d, P.q32, P.pair_query, P.bws);
+  tc_fill_pairs_kernel<<<(unsigned)cdiv(P.npairs * 32, 256), 256, 0, s>>>(probes, P.pos, P.pair_off, v.list_len, P.npairs, nprobe, d, P.q32, P.pair_query, P.bws);
   tc_items_kernel<<<(unsigned)cdiv(v.nlist, 128), 128, 0, s>>>(P.cnt, v.list_len, P.pair_off, P.item_off, v.nlist, P.items, P.totals, P.sample_list);
   B200VS_CUDA(cudaGetLastError());
   P.tmA = make_tmap(v.vecs, v.arena_rows, d, TC_BM);
@@ -1002,7 +1045,7 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
     timer.stop();
   }
   // 3) window select + exact rerank + certification
-  const size_t fast_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_MAXW * 12 + (size_t)next_pow2(cap) * 8;
+  const size_t fast_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_MAXW * 16 + (size_t)cap * 8;
   if (fast_smem <= 200 * 1024) {  // one 64-bit sort of the captured rows + a small exact sort
     if (l2) tc_final_fast_kernel<true><<<(unsigned)nq, SCAN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
     else tc_final_fast_kernel<false><<<(unsigned)nq, SCAN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
@@ -1071,7 +1114,7 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   B200VS_CUDA(cudaGetLastError());
   if (nrows <= COARSE_FAST && nprobe <= nrows) {
     const int maxw = std::max(2, next_pow2(nrows));
-    const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)maxw * 20;
+    const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)maxw * 24;
     if (l2) tc_coarse_final_fast_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, out_probes, out_raw);
     else tc_coarse_final_fast_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, out_probes, out_raw);
   } else {
