@@ -57,6 +57,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
+// gather4: four arbitrary rows (r0..r3) of a 2-D tensor, `box` columns each, land as four consecutive smem rows
+__device__ __forceinline__ void tma_gather4_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int r0, int r1, int r2, int r3,
+                                               uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "l"(policy)
+      : "memory");
+}
 // L2 eviction policies (createpolicy encodings used by CUTLASS' TMA::CacheHintSm90)
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;

@@ -13,6 +13,7 @@
 //   tc_compact_flags_kernel  list of uncertified queries for the exact re-run
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "scan_kernels.cuh"
 #include "sm100_ptx.cuh"
@@ -157,6 +158,7 @@ static __global__ void tc_fill_pairs_kernel(const long long* __restrict__ probes
   const int p = pair_off[l] + pos[w];
   const int q = (int)(w / nprobe);
   if (lane == 0) pair_query[p] = q;
+  if (!bws) return;  // gather4 mode: the scan kernel reads the query rows directly
   const float4* src = reinterpret_cast<const float4*>(q32 + (size_t)q * d);
   float4* dst = reinterpret_cast<float4*>(bws + (size_t)p * d);
   for (int i = lane; i < (d >> 2); i += 32) dst[i] = src[i];
@@ -206,7 +208,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmB16, const __grid_constant__ CUtensorMap tmB32,
                const __grid_constant__ CUtensorMap tmB64, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmBlo16, const __grid_constant__ CUtensorMap tmBlo32,
-               const __grid_constant__ CUtensorMap tmBlo64, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmBlo64, const __grid_constant__ CUtensorMap tmQ, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -217,6 +219,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ uint32_t s_tmem_base;
   __shared__ float s_tau[2][TC_NQT];
   __shared__ int s_q[2][TC_NQT];
+  __shared__ int s_brow[TC_NQT];  // producer-private: query rows of the current item (gather4 mode)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmA32); prefetch_tmap(&tmB16); prefetch_tmap(&tmB32); prefetch_tmap(&tmB64); }
@@ -256,11 +259,22 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const CUtensorMap* ta = p.mode == 0 ? &tmA32 : &tmA;
         const uint32_t bytes = (p.mode == 0 ? (uint32_t)(TC_SAMPLE * 128) : TC_A_BYTES) + (uint32_t)b_rows * 128u;
         const CUtensorMap* tbl = I.nq <= 16 ? &tmBlo16 : (I.nq <= 32 ? &tmBlo32 : &tmBlo64);
+        const int npad_b = max(16, (I.nq + 15) & ~15);
+        uint32_t bytes_g = bytes;
+        if (p.b_gather) {
+          for (int j = 0; j < npad_b; ++j) s_brow[j] = j < I.nq ? p.pair_query[I.pair_begin + j] : 0;
+          bytes_g = (p.mode == 0 ? (uint32_t)(TC_SAMPLE * 128) : TC_A_BYTES) + (uint32_t)npad_b * 128u;
+        }
         for (int t = 0; t < ntiles; ++t)
           for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            mbar_arrive_expect_tx(&full_bar[stage], p.b_gather ? bytes_g : bytes);
             tma_load_2d(sA + (size_t)stage * TC_A_BYTES, ta, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
+            if (p.b_gather) {
+              uint8_t* bdst = sB + (size_t)stage * TC_B_BYTES;
+              for (int g = 0; g < npad_b; g += 4)
+                tma_gather4_2d(bdst + (size_t)g * 128, &tmQ, &full_bar[stage], kb * TC_BK, s_brow[g], s_brow[g + 1], s_brow[g + 2], s_brow[g + 3], kEvictLast);
+            } else
             tma_load_2d(sB + (size_t)stage * TC_B_BYTES, tb, &full_bar[stage], kb * TC_BK, I.pair_begin, kEvictLast);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
             if (p.split) {  // error-compensated pass: the "lo" operands ride in the next ring stage
@@ -954,7 +968,8 @@ struct TcPlan {
   float* bws;
   TcItem* items;
   int64_t bound, sbound, npairs;
-  CUtensorMap tmA, tmA32, tmB16, tmB32, tmB64;
+  CUtensorMap tmA, tmA32, tmB16, tmB32, tmB64, tmQ;
+  bool gather;
 };
 
 static TcPlan tc_prepare(IndexBase* ix, const TcView& v, int64_t nq, const float* q, const long long* probes, int nprobe, cudaStream_t s) {
@@ -982,7 +997,9 @@ static TcPlan tc_prepare(IndexBase* ix, const TcView& v, int64_t nq, const float
   tc_prep_queries_kernel<<<(unsigned)cdiv(nq * 32, 256), 256, 0, s>>>(q, nq, d, P.q32, P.qnorm);
   tc_count_pairs_kernel<<<(unsigned)cdiv(P.npairs, 256), 256, 0, s>>>(probes, P.npairs, P.cnt, P.pos);
   tc_plan_kernel<<<1, 1024, 0, s>>>(P.cnt, v.list_len, v.nlist, P.pair_off, P.item_off, P.totals);
-  tc_fill_pairs_kernel<<<(unsigned)cdiv(P.npairs * 32, 256), 256, 0, s>>>(probes, P.pos, P.pair_off, v.list_len, P.npairs, nprobe, d, P.q32, P.pair_query, P.bws);
+  static const bool use_gather4 = getenv("B200VS_GATHER4") && atoi(getenv("B200VS_GATHER4")) != 0;
+  P.gather = use_gather4;
+  tc_fill_pairs_kernel<<<(unsigned)cdiv(P.npairs * 32, 256), 256, 0, s>>>(probes, P.pos, P.pair_off, v.list_len, P.npairs, nprobe, d, P.q32, P.pair_query, P.gather ? nullptr : P.bws);
   tc_items_kernel<<<(unsigned)cdiv(v.nlist, 128), 128, 0, s>>>(P.cnt, v.list_len, P.pair_off, P.item_off, v.nlist, P.items, P.totals, P.sample_list);
   B200VS_CUDA(cudaGetLastError());
   P.tmA = make_tmap(v.vecs, v.arena_rows, d, TC_BM);
@@ -990,6 +1007,7 @@ static TcPlan tc_prepare(IndexBase* ix, const TcView& v, int64_t nq, const float
   P.tmB16 = make_tmap(P.bws, P.npairs + TC_NQT, d, 16);
   P.tmB32 = make_tmap(P.bws, P.npairs + TC_NQT, d, 32);
   P.tmB64 = make_tmap(P.bws, P.npairs + TC_NQT, d, 64);
+  P.tmQ = make_tmap(P.q32, nq, d, 1);  // gather4 source: one row per box
   ix->launch_count(5);
   return P;
 }
@@ -998,13 +1016,13 @@ static TcParams tc_params(const TcView& v, const TcPlan& P, int d, bool l2) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.ids = v.ids; p.norms = v.norms; p.list_off = v.list_off; p.d = d; p.items = P.items; p.totals = P.totals;
-  p.sample_list = P.sample_list; p.pair_query = P.pair_query; p.l2 = l2 ? 1 : 0; p.add_norm = 1;
+  p.sample_list = P.sample_list; p.pair_query = P.pair_query; p.l2 = l2 ? 1 : 0; p.add_norm = 1; p.b_gather = P.gather ? 1 : 0;
   return p;
 }
 
 static void tc_launch(const TcPlan& P, const TcParams& p, int64_t work_bound, cudaStream_t s) {
   const int grid = (int)std::min<int64_t>(g_num_sms, std::max<int64_t>(1, work_bound));
-  tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(P.tmA, P.tmA32, P.tmB16, P.tmB32, P.tmB64, P.tmA, P.tmB16, P.tmB32, P.tmB64, p);
+  tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(P.tmA, P.tmA32, P.tmB16, P.tmB32, P.tmB64, P.tmA, P.tmB16, P.tmB32, P.tmB64, P.tmQ, p);
   B200VS_CUDA(cudaGetLastError());
 }
 
@@ -1110,7 +1128,7 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   const CUtensorMap l16 = make_tmap(qlo, nq, d, 16), l32 = make_tmap(qlo, nq, d, 32), l64 = make_tmap(qlo, nq, d, 64);
   const int grid = (int)std::min<int64_t>(g_num_sms, std::max(1, nitems));
   p.work_counter = work; p.split = 1; p.dense_accum = 0; p.add_norm = 1;
-  tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(a_hi, a_hi, b16, b32, b64, a_lo, l16, l32, l64, p);
+  tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(a_hi, a_hi, b16, b32, b64, a_lo, l16, l32, l64, b16, p);
   B200VS_CUDA(cudaGetLastError());
   if (nrows <= COARSE_FAST && nprobe <= nrows) {
     const int maxw = std::max(2, next_pow2(nrows));

@@ -63,6 +63,7 @@ struct TcParams {
   long long dense_ld;
   int dense_accum;          // mode 2: add to the stored score instead of overwriting (split-precision passes 2 and 3)
   int add_norm;             // include the ||x||^2 term (off for the correction passes)
+  int b_gather;             // B tiles gathered straight from the rounded query matrix with TMA gather4 (no gathered copy)
   int split;                // error-compensated TF32: hi*hi + lo*hi + hi*lo into one accumulator (coarse quantiser)
   int l2;
   FilterDev filt;
