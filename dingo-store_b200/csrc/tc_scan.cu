@@ -212,7 +212,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)TC_STAGES * TC_A_BYTES;
+  uint8_t* sB = smem + (size_t)TC_STAGES * TC_A_STAGE;
   __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ __align__(8) uint64_t sched_full[TC_SQ], sched_empty[TC_SQ];
   __shared__ int s_sched[TC_SQ];
@@ -229,7 +229,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < TC_SQ; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 5); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&s_tmem_base, 2 * TC_NQT);
+  if (warp == 2) tmem_alloc(&s_tmem_base, 2 * TC_TILES * TC_NQT);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -257,34 +257,34 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int b_rows = I.nq <= 16 ? 16 : (I.nq <= 32 ? 32 : 64);
         const CUtensorMap* tb = I.nq <= 16 ? &tmB16 : (I.nq <= 32 ? &tmB32 : &tmB64);
         const CUtensorMap* ta = p.mode == 0 ? &tmA32 : &tmA;
-        const uint32_t bytes = (p.mode == 0 ? (uint32_t)(TC_SAMPLE * 128) : TC_A_BYTES) + (uint32_t)b_rows * 128u;
+        const uint32_t a_bytes = p.mode == 0 ? (uint32_t)(TC_SAMPLE * 128) : (uint32_t)ntiles * TC_A_BYTES;
         const CUtensorMap* tbl = I.nq <= 16 ? &tmBlo16 : (I.nq <= 32 ? &tmBlo32 : &tmBlo64);
         const int npad_b = max(16, (I.nq + 15) & ~15);
-        uint32_t bytes_g = bytes;
-        if (p.b_gather) {
+        if (p.b_gather)
           for (int j = 0; j < npad_b; ++j) s_brow[j] = j < I.nq ? p.pair_query[I.pair_begin + j] : 0;
-          bytes_g = (p.mode == 0 ? (uint32_t)(TC_SAMPLE * 128) : TC_A_BYTES) + (uint32_t)npad_b * 128u;
-        }
-        for (int t = 0; t < ntiles; ++t)
-          for (int kb = 0; kb < kblocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], p.b_gather ? bytes_g : bytes);
-            tma_load_2d(sA + (size_t)stage * TC_A_BYTES, ta, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
-            if (p.b_gather) {
-              uint8_t* bdst = sB + (size_t)stage * TC_B_BYTES;
-              for (int g = 0; g < npad_b; g += 4)
-                tma_gather4_2d(bdst + (size_t)g * 128, &tmQ, &full_bar[stage], kb * TC_BK, s_brow[g], s_brow[g + 1], s_brow[g + 2], s_brow[g + 3], kEvictLast);
-            } else
+        const uint32_t bytes = a_bytes + (p.b_gather ? (uint32_t)npad_b : (uint32_t)b_rows) * 128u;
+        for (int kb = 0; kb < kblocks; ++kb) {  // K outer: the B tile of a K block is loaded once for all row tiles
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], bytes);
+          for (int t = 0; t < ntiles; ++t)
+            tma_load_2d(sA + (size_t)stage * TC_A_STAGE + (size_t)t * TC_A_BYTES, ta, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
+          if (p.b_gather) {
+            uint8_t* bdst = sB + (size_t)stage * TC_B_BYTES;
+            for (int g = 0; g < npad_b; g += 4)
+              tma_gather4_2d(bdst + (size_t)g * 128, &tmQ, &full_bar[stage], kb * TC_BK, s_brow[g], s_brow[g + 1], s_brow[g + 2], s_brow[g + 3], kEvictLast);
+          } else {
             tma_load_2d(sB + (size_t)stage * TC_B_BYTES, tb, &full_bar[stage], kb * TC_BK, I.pair_begin, kEvictLast);
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-            if (p.split) {  // error-compensated pass: the "lo" operands ride in the next ring stage
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full_bar[stage], bytes);
-              tma_load_2d(sA + (size_t)stage * TC_A_BYTES, &tmAlo, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
-              tma_load_2d(sB + (size_t)stage * TC_B_BYTES, tbl, &full_bar[stage], kb * TC_BK, I.pair_begin, kEvictLast);
-              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-            }
           }
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (p.split) {  // error-compensated pass: the "lo" operands ride in the next ring stage
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            for (int t = 0; t < ntiles; ++t)
+              tma_load_2d(sA + (size_t)stage * TC_A_STAGE + (size_t)t * TC_A_BYTES, &tmAlo, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
+            tma_load_2d(sB + (size_t)stage * TC_B_BYTES, tbl, &full_bar[stage], kb * TC_BK, I.pair_begin, kEvictLast);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -303,30 +303,38 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ntiles = (rows + TC_BM - 1) / TC_BM;
         const uint32_t npad = (uint32_t)max(16, (I.nq + 15) & ~15);
         const uint32_t idesc = make_idesc_tf32(TC_BM, npad);
-        for (int t = 0; t < ntiles; ++t, ++tcount) {
-          const uint32_t acc = tcount & 1, aphase = (tcount >> 1) & 1;
+        {
+          const uint32_t acc = tcount & 1, aphase = (tcount >> 1) & 1;  // one accumulator buffer (TC_TILES x 64 columns) per item
+          ++tcount;
           mbar_wait(&tempty_bar[acc], aphase ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * TC_NQT;
+          const uint32_t d_tmem = tmem_base + acc * (TC_TILES * TC_NQT);
           for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint64_t adesc = make_desc_k128(smem_u32(sA + (size_t)stage * TC_A_BYTES));
+            const uint32_t a_base = smem_u32(sA + (size_t)stage * TC_A_STAGE);
             const uint64_t bdesc = make_desc_k128(smem_u32(sB + (size_t)stage * TC_B_BYTES));
+            for (int t = 0; t < ntiles; ++t) {
+              const uint64_t adesc = make_desc_k128(a_base + (uint32_t)t * TC_A_BYTES);
 #pragma unroll
-            for (int k = 0; k < TC_BK / 8; ++k)  // UMMA K = 8 TF32 = 32 B: advance the start address by 2 (>>4 units)
-              umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < TC_BK / 8; ++k)  // UMMA K = 8 TF32 = 32 B: advance the start address by 2 (>>4 units)
+                umma_tf32(d_tmem + t * TC_NQT, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
             const int stage_hi = stage;
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-            if (p.split) {  // + lo*hi + hi*lo into the same accumulator
+            if (p.split) {  // + lo*hi + hi*lo into the same accumulators
               mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
-              const uint64_t adesc_lo = make_desc_k128(smem_u32(sA + (size_t)stage * TC_A_BYTES));
+              const uint32_t a_lo = smem_u32(sA + (size_t)stage * TC_A_STAGE);
               const uint64_t bdesc_lo = make_desc_k128(smem_u32(sB + (size_t)stage * TC_B_BYTES));
+              for (int t = 0; t < ntiles; ++t) {
+                const uint64_t adesc = make_desc_k128(a_base + (uint32_t)t * TC_A_BYTES);
+                const uint64_t adesc_lo = make_desc_k128(a_lo + (uint32_t)t * TC_A_BYTES);
 #pragma unroll
-              for (int k = 0; k < TC_BK / 8; ++k) {
-                umma_tf32(d_tmem, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
-                umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc, 1u);
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                  umma_tf32(d_tmem + t * TC_NQT, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                  umma_tf32(d_tmem + t * TC_NQT, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc, 1u);
+                }
               }
               umma_commit(&empty_bar[stage_hi]);
               umma_commit(&empty_bar[stage]);
@@ -335,7 +343,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               umma_commit(&empty_bar[stage_hi]);  // frees the smem slot when these MMAs retire
             }
           }
-          umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
+          umma_commit(&tfull_bar[acc]);  // all accumulators of the item are ready for the epilogue
         }
       }
     }
@@ -365,8 +373,11 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.mode == 0) rows = min(rows, TC_SAMPLE);
       const int ntiles = (rows + TC_BM - 1) / TC_BM;
       const int npad = max(16, (I.nq + 15) & ~15);
-      for (int t = 0; t < ntiles; ++t, ++tcount) {
-        const uint32_t acc = tcount & 1, aphase = (tcount >> 1) & 1;
+      const uint32_t acc = tcount & 1, aphase = (tcount >> 1) & 1;
+      ++tcount;
+      mbar_wait(&tfull_bar[acc], aphase);
+      tc_fence_after();
+      for (int t = 0; t < ntiles; ++t) {
         const int r = t * TC_BM + ew * 32 + lane;  // row within the item
         const bool inrange = r < rows;
         bool valid = inrange;
@@ -377,9 +388,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           valid = id >= 0 && filter_pass(p.filt, id);
           if (valid && p.l2 && p.add_norm) nrm = p.norms[arow];
         }
-        mbar_wait(&tfull_bar[acc], aphase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TC_NQT;
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * (TC_TILES * TC_NQT) + t * TC_NQT;
         for (int c0 = 0; c0 < npad; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
@@ -406,15 +415,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * TC_NQT); }
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * TC_TILES * TC_NQT); }
 }
 
 // ---------------------------------------------------------------------------------------------
