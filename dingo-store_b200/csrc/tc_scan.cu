@@ -206,13 +206,14 @@ static __global__ void tc_items_kernel(const int* __restrict__ cnt, const int* _
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA32,
                const __grid_constant__ CUtensorMap tmB16, const __grid_constant__ CUtensorMap tmB32,
-               const __grid_constant__ CUtensorMap tmB64, const __grid_constant__ CUtensorMap tmAlo,
-               const __grid_constant__ CUtensorMap tmBlo16, const __grid_constant__ CUtensorMap tmBlo32,
-               const __grid_constant__ CUtensorMap tmBlo64, const __grid_constant__ CUtensorMap tmQ, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmB64, const __grid_constant__ CUtensorMap tmB128,
+               const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo16,
+               const __grid_constant__ CUtensorMap tmBlo32, const __grid_constant__ CUtensorMap tmBlo64,
+               const __grid_constant__ CUtensorMap tmBlo128, const __grid_constant__ CUtensorMap tmQ, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)TC_STAGES * TC_A_STAGE;
+  uint8_t* sB = smem + (size_t)TC_STAGES * TC_A_BYTES;
   __shared__ __align__(8) uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ __align__(8) uint64_t sched_full[TC_SQ], sched_empty[TC_SQ];
   __shared__ int s_sched[TC_SQ];
@@ -222,14 +223,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ int s_brow[TC_NQT];  // producer-private: query rows of the current item (gather4 mode)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmA32); prefetch_tmap(&tmB16); prefetch_tmap(&tmB32); prefetch_tmap(&tmB64); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmA32); prefetch_tmap(&tmB16); prefetch_tmap(&tmB32); prefetch_tmap(&tmB64); prefetch_tmap(&tmB128); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
     for (int i = 0; i < TC_SQ; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 5); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&s_tmem_base, 2 * TC_TILES * TC_NQT);
+  if (warp == 2) tmem_alloc(&s_tmem_base, 2 * TC_NQT);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -254,37 +255,37 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int rows = I.row_end - I.row_begin;
         if (p.mode == 0) rows = min(rows, TC_SAMPLE);
         const int ntiles = (rows + TC_BM - 1) / TC_BM;
-        const int b_rows = I.nq <= 16 ? 16 : (I.nq <= 32 ? 32 : 64);
-        const CUtensorMap* tb = I.nq <= 16 ? &tmB16 : (I.nq <= 32 ? &tmB32 : &tmB64);
+        const int b_rows = I.nq <= 16 ? 16 : (I.nq <= 32 ? 32 : (I.nq <= 64 ? 64 : 128));
+        const CUtensorMap* tb = I.nq <= 16 ? &tmB16 : (I.nq <= 32 ? &tmB32 : (I.nq <= 64 ? &tmB64 : &tmB128));
         const CUtensorMap* ta = p.mode == 0 ? &tmA32 : &tmA;
-        const uint32_t a_bytes = p.mode == 0 ? (uint32_t)(TC_SAMPLE * 128) : (uint32_t)ntiles * TC_A_BYTES;
-        const CUtensorMap* tbl = I.nq <= 16 ? &tmBlo16 : (I.nq <= 32 ? &tmBlo32 : &tmBlo64);
+        const uint32_t bytes = (p.mode == 0 ? (uint32_t)(TC_SAMPLE * 128) : TC_A_BYTES) + (uint32_t)b_rows * 128u;
+        const CUtensorMap* tbl = I.nq <= 16 ? &tmBlo16 : (I.nq <= 32 ? &tmBlo32 : (I.nq <= 64 ? &tmBlo64 : &tmBlo128));
         const int npad_b = max(16, (I.nq + 15) & ~15);
-        if (p.b_gather)
+        uint32_t bytes_g = bytes;
+        if (p.b_gather) {
           for (int j = 0; j < npad_b; ++j) s_brow[j] = j < I.nq ? p.pair_query[I.pair_begin + j] : 0;
-        const uint32_t bytes = a_bytes + (p.b_gather ? (uint32_t)npad_b : (uint32_t)b_rows) * 128u;
-        for (int kb = 0; kb < kblocks; ++kb) {  // K outer: the B tile of a K block is loaded once for all row tiles
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], bytes);
-          for (int t = 0; t < ntiles; ++t)
-            tma_load_2d(sA + (size_t)stage * TC_A_STAGE + (size_t)t * TC_A_BYTES, ta, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
-          if (p.b_gather) {
-            uint8_t* bdst = sB + (size_t)stage * TC_B_BYTES;
-            for (int g = 0; g < npad_b; g += 4)
-              tma_gather4_2d(bdst + (size_t)g * 128, &tmQ, &full_bar[stage], kb * TC_BK, s_brow[g], s_brow[g + 1], s_brow[g + 2], s_brow[g + 3], kEvictLast);
-          } else {
-            tma_load_2d(sB + (size_t)stage * TC_B_BYTES, tb, &full_bar[stage], kb * TC_BK, I.pair_begin, kEvictLast);
-          }
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-          if (p.split) {  // error-compensated pass: the "lo" operands ride in the next ring stage
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], bytes);
-            for (int t = 0; t < ntiles; ++t)
-              tma_load_2d(sA + (size_t)stage * TC_A_STAGE + (size_t)t * TC_A_BYTES, &tmAlo, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
-            tma_load_2d(sB + (size_t)stage * TC_B_BYTES, tbl, &full_bar[stage], kb * TC_BK, I.pair_begin, kEvictLast);
-            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-          }
+          bytes_g = (p.mode == 0 ? (uint32_t)(TC_SAMPLE * 128) : TC_A_BYTES) + (uint32_t)npad_b * 128u;
         }
+        for (int t = 0; t < ntiles; ++t)
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], p.b_gather ? bytes_g : bytes);
+            tma_load_2d(sA + (size_t)stage * TC_A_BYTES, ta, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
+            if (p.b_gather) {
+              uint8_t* bdst = sB + (size_t)stage * TC_B_BYTES;
+              for (int g = 0; g < npad_b; g += 4)
+                tma_gather4_2d(bdst + (size_t)g * 128, &tmQ, &full_bar[stage], kb * TC_BK, s_brow[g], s_brow[g + 1], s_brow[g + 2], s_brow[g + 3], kEvictLast);
+            } else
+            tma_load_2d(sB + (size_t)stage * TC_B_BYTES, tb, &full_bar[stage], kb * TC_BK, I.pair_begin, kEvictLast);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            if (p.split) {  // error-compensated pass: the "lo" operands ride in the next ring stage
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[stage], bytes);
+              tma_load_2d(sA + (size_t)stage * TC_A_BYTES, &tmAlo, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
+              tma_load_2d(sB + (size_t)stage * TC_B_BYTES, tbl, &full_bar[stage], kb * TC_BK, I.pair_begin, kEvictLast);
+              if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
       }
     }
   } else if (warp == 1) {
@@ -303,38 +304,30 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ntiles = (rows + TC_BM - 1) / TC_BM;
         const uint32_t npad = (uint32_t)max(16, (I.nq + 15) & ~15);
         const uint32_t idesc = make_idesc_tf32(TC_BM, npad);
-        {
-          const uint32_t acc = tcount & 1, aphase = (tcount >> 1) & 1;  // one accumulator buffer (TC_TILES x 64 columns) per item
-          ++tcount;
+        for (int t = 0; t < ntiles; ++t, ++tcount) {
+          const uint32_t acc = tcount & 1, aphase = (tcount >> 1) & 1;
           mbar_wait(&tempty_bar[acc], aphase ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * (TC_TILES * TC_NQT);
+          const uint32_t d_tmem = tmem_base + acc * TC_NQT;
           for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(sA + (size_t)stage * TC_A_STAGE);
+            const uint64_t adesc = make_desc_k128(smem_u32(sA + (size_t)stage * TC_A_BYTES));
             const uint64_t bdesc = make_desc_k128(smem_u32(sB + (size_t)stage * TC_B_BYTES));
-            for (int t = 0; t < ntiles; ++t) {
-              const uint64_t adesc = make_desc_k128(a_base + (uint32_t)t * TC_A_BYTES);
 #pragma unroll
-              for (int k = 0; k < TC_BK / 8; ++k)  // UMMA K = 8 TF32 = 32 B: advance the start address by 2 (>>4 units)
-                umma_tf32(d_tmem + t * TC_NQT, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < TC_BK / 8; ++k)  // UMMA K = 8 TF32 = 32 B: advance the start address by 2 (>>4 units)
+              umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
             const int stage_hi = stage;
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-            if (p.split) {  // + lo*hi + hi*lo into the same accumulators
+            if (p.split) {  // + lo*hi + hi*lo into the same accumulator
               mbar_wait(&full_bar[stage], phase);
               tc_fence_after();
-              const uint32_t a_lo = smem_u32(sA + (size_t)stage * TC_A_STAGE);
+              const uint64_t adesc_lo = make_desc_k128(smem_u32(sA + (size_t)stage * TC_A_BYTES));
               const uint64_t bdesc_lo = make_desc_k128(smem_u32(sB + (size_t)stage * TC_B_BYTES));
-              for (int t = 0; t < ntiles; ++t) {
-                const uint64_t adesc = make_desc_k128(a_base + (uint32_t)t * TC_A_BYTES);
-                const uint64_t adesc_lo = make_desc_k128(a_lo + (uint32_t)t * TC_A_BYTES);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {
-                  umma_tf32(d_tmem + t * TC_NQT, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
-                  umma_tf32(d_tmem + t * TC_NQT, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc, 1u);
-                }
+              for (int k = 0; k < TC_BK / 8; ++k) {
+                umma_tf32(d_tmem, adesc_lo + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                umma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc_lo + (uint64_t)(2 * k), idesc, 1u);
               }
               umma_commit(&empty_bar[stage_hi]);
               umma_commit(&empty_bar[stage]);
@@ -343,7 +336,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               umma_commit(&empty_bar[stage_hi]);  // frees the smem slot when these MMAs retire
             }
           }
-          umma_commit(&tfull_bar[acc]);  // all accumulators of the item are ready for the epilogue
+          umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
         }
       }
     }
@@ -373,11 +366,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.mode == 0) rows = min(rows, TC_SAMPLE);
       const int ntiles = (rows + TC_BM - 1) / TC_BM;
       const int npad = max(16, (I.nq + 15) & ~15);
-      const uint32_t acc = tcount & 1, aphase = (tcount >> 1) & 1;
-      ++tcount;
-      mbar_wait(&tfull_bar[acc], aphase);
-      tc_fence_after();
-      for (int t = 0; t < ntiles; ++t) {
+      for (int t = 0; t < ntiles; ++t, ++tcount) {
+        const uint32_t acc = tcount & 1, aphase = (tcount >> 1) & 1;
         const int r = t * TC_BM + ew * 32 + lane;  // row within the item
         const bool inrange = r < rows;
         bool valid = inrange;
@@ -388,7 +378,9 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           valid = id >= 0 && filter_pass(p.filt, id);
           if (valid && p.l2 && p.add_norm) nrm = p.norms[arow];
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * (TC_TILES * TC_NQT) + t * TC_NQT;
+        mbar_wait(&tfull_bar[acc], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * TC_NQT;
         for (int c0 = 0; c0 < npad; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
@@ -415,15 +407,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * TC_TILES * TC_NQT); }
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * TC_NQT); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -622,7 +614,8 @@ __device__ int window_select(const unsigned long long* keys, int n, int k, float
       asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
     }
   }
-  for (int base = 0; base < m; base += SCAN_QUADS) {
+  const int nquads = blockDim.x >> 2;
+  for (int base = 0; base < m; base += nquads) {
     const int i = base + quad;
     const bool valid = i < m;
     const long long row = (long long)(uint32_t)rows[valid ? i : 0];
@@ -638,6 +631,7 @@ __device__ int window_select(const unsigned long long* keys, int n, int k, float
   return min(m, k);
 }
 
+constexpr int FIN_THREADS = 128;   // finish kernels: many small CTAs hide their barrier / gather latency better than few big ones
 constexpr int FIN_MAXW = 1024;     // in-window rows re-scored per query on the fast path (more -> exact re-run)
 constexpr int COARSE_FAST = 4096;  // coarse rows handled by the one-sort path
 
@@ -977,7 +971,7 @@ struct TcPlan {
   float* bws;
   TcItem* items;
   int64_t bound, sbound, npairs;
-  CUtensorMap tmA, tmA32, tmB16, tmB32, tmB64, tmQ;
+  CUtensorMap tmA, tmA32, tmB16, tmB32, tmB64, tmB128, tmQ;
   bool gather;
 };
 
@@ -1016,6 +1010,7 @@ static TcPlan tc_prepare(IndexBase* ix, const TcView& v, int64_t nq, const float
   P.tmB16 = make_tmap(P.bws, P.npairs + TC_NQT, d, 16);
   P.tmB32 = make_tmap(P.bws, P.npairs + TC_NQT, d, 32);
   P.tmB64 = make_tmap(P.bws, P.npairs + TC_NQT, d, 64);
+  P.tmB128 = make_tmap(P.bws, P.npairs + TC_NQT, d, 128);
   P.tmQ = make_tmap(P.q32, nq, d, 1);  // gather4 source: one row per box
   ix->launch_count(5);
   return P;
@@ -1031,7 +1026,7 @@ static TcParams tc_params(const TcView& v, const TcPlan& P, int d, bool l2) {
 
 static void tc_launch(const TcPlan& P, const TcParams& p, int64_t work_bound, cudaStream_t s) {
   const int grid = (int)std::min<int64_t>(g_num_sms, std::max<int64_t>(1, work_bound));
-  tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(P.tmA, P.tmA32, P.tmB16, P.tmB32, P.tmB64, P.tmA, P.tmB16, P.tmB32, P.tmB64, P.tmQ, p);
+  tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(P.tmA, P.tmA32, P.tmB16, P.tmB32, P.tmB64, P.tmB128, P.tmA, P.tmB16, P.tmB32, P.tmB64, P.tmB128, P.tmQ, p);
   B200VS_CUDA(cudaGetLastError());
 }
 
@@ -1074,8 +1069,8 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   // 3) window select + exact rerank + certification
   const size_t fast_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_MAXW * 16 + (size_t)cap * 8;
   if (fast_smem <= 200 * 1024) {  // one 64-bit sort of the captured rows + a small exact sort
-    if (l2) tc_final_fast_kernel<true><<<(unsigned)nq, SCAN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
-    else tc_final_fast_kernel<false><<<(unsigned)nq, SCAN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
+    if (l2) tc_final_fast_kernel<true><<<(unsigned)nq, FIN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
+    else tc_final_fast_kernel<false><<<(unsigned)nq, FIN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
   } else {
     const size_t fin_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + sel_smem;
     if (l2) tc_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags);
@@ -1133,17 +1128,17 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   TcParams p = tc_params(v, P, d, l2);
   p.mode = 2; p.dense = dense; p.dense_ld = nrows; p.pair_query = nullptr;
   const CUtensorMap a_hi = make_tmap(v.vecs_hi, nrows, d, TC_BM), a_lo = make_tmap(v.vecs_lo, nrows, d, TC_BM);
-  const CUtensorMap b16 = make_tmap(qhi, nq, d, 16), b32 = make_tmap(qhi, nq, d, 32), b64 = make_tmap(qhi, nq, d, 64);
-  const CUtensorMap l16 = make_tmap(qlo, nq, d, 16), l32 = make_tmap(qlo, nq, d, 32), l64 = make_tmap(qlo, nq, d, 64);
+  const CUtensorMap b16 = make_tmap(qhi, nq, d, 16), b32 = make_tmap(qhi, nq, d, 32), b64 = make_tmap(qhi, nq, d, 64), b128 = make_tmap(qhi, nq, d, 128);
+  const CUtensorMap l16 = make_tmap(qlo, nq, d, 16), l32 = make_tmap(qlo, nq, d, 32), l64 = make_tmap(qlo, nq, d, 64), l128 = make_tmap(qlo, nq, d, 128);
   const int grid = (int)std::min<int64_t>(g_num_sms, std::max(1, nitems));
   p.work_counter = work; p.split = 1; p.dense_accum = 0; p.add_norm = 1;
-  tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(a_hi, a_hi, b16, b32, b64, a_lo, l16, l32, l64, b16, p);
+  tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(a_hi, a_hi, b16, b32, b64, b128, a_lo, l16, l32, l64, l128, b16, p);
   B200VS_CUDA(cudaGetLastError());
   if (nrows <= COARSE_FAST && nprobe <= nrows) {
     const int maxw = std::max(2, next_pow2(nrows));
     const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)maxw * 24;
-    if (l2) tc_coarse_final_fast_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, out_probes, out_raw);
-    else tc_coarse_final_fast_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, out_probes, out_raw);
+    if (l2) tc_coarse_final_fast_kernel<true><<<(unsigned)nq, FIN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, out_probes, out_raw);
+    else tc_coarse_final_fast_kernel<false><<<(unsigned)nq, FIN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, out_probes, out_raw);
   } else {
     const int pool = select_pool_cap(nprobe, SCAN_THREADS);
     const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + BlockSelect::smem_bytes(pool);

@@ -23,19 +23,16 @@ namespace b200vs {
 
 constexpr int TC_BM = 128;        // database rows per MMA tile (UMMA M)
 constexpr int TC_BK = 32;         // floats per K block = 128 B = one swizzle span
-constexpr int TC_NQT = 64;        // queries per work item (UMMA N <= 64)
-constexpr int TC_TILES = 4;       // row tiles per work item that share one B (query) tile load per K block
-constexpr int TC_STAGES = 2;      // TMA->MMA ring depth (each stage: TC_TILES A tiles + one B tile = 72 KB)
+constexpr int TC_NQT = 128;       // queries per work item (UMMA N <= 128): a probed list chunk is re-streamed only beyond 128 queries
+constexpr int TC_STAGES = 5;      // TMA->MMA ring depth (5 x 32 KB: leaves ~65 KB of shared memory per SM for co-resident small kernels)
 constexpr int TC_THREADS = 256;   // warp0 TMA + scheduler, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
 constexpr int TC_CHUNK = 512;     // rows per work item (list chunk): fine grain for dynamic load balance
 constexpr int TC_SPAN = 2048;     // one sampled chunk per TC_SPAN rows of a list
 constexpr int TC_SAMPLE = 32;     // sampled rows per span for the threshold estimate
 constexpr int TC_SQ = 4;          // scheduler queue depth (items the producer may run ahead)
-constexpr uint32_t TC_A_BYTES = TC_BM * 128;               // one A tile
-constexpr uint32_t TC_A_STAGE = TC_TILES * TC_A_BYTES;      // A area of a stage
+constexpr uint32_t TC_A_BYTES = TC_BM * 128;
 constexpr uint32_t TC_B_BYTES = TC_NQT * 128;
-constexpr size_t TC_SMEM = (size_t)TC_STAGES * (TC_A_STAGE + TC_B_BYTES) + 1024;
-static_assert(TC_CHUNK == TC_TILES * TC_BM, "a work item is TC_TILES row tiles");
+constexpr size_t TC_SMEM = (size_t)TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 1024;
 
 struct TcItem {
   int list;
