@@ -452,7 +452,12 @@ struct HnswIndex : IndexBase {
     memcpy(H.labels.data(), p, n * 8);
     if ((size_t)(p - base) + (size_t)n * 8 > len) fail(B200VS_EILLEGAL_PARAMETERS, "state blob truncated");
     H.n = n; H.maxlevel = (int)hdr[5]; H.enterpoint = (tableint)hdr[6];
-    for (int64_t i = 0; i < n; ++i) H.lookup[H.labels[i]] = (tableint)i;
+    const size_t after_labels = (size_t)(p - base) + (size_t)n * 8;
+    if (len >= after_labels + (size_t)n) {  // optional trailing tombstone bytes (written only when something was deleted)
+      memcpy(H.deleted.data(), base + after_labels, (size_t)n);
+      for (int64_t i = 0; i < n; ++i) H.ndeleted += H.deleted[i] ? 1 : 0;
+    }
+    for (int64_t i = 0; i < n; ++i) if (!H.deleted[i]) H.lookup[H.labels[i]] = (tableint)i;
     G = std::move(H);
     dirty = true; uploaded_rows = 0;
   }
@@ -581,6 +586,7 @@ struct HnswIndex : IndexBase {
     sz = pad8(sz + (n + 1) * 8 + n * (int64_t)(G.maxM0 + 1) * 4 + up * 4);
     sz = pad8(sz + n * (int64_t)dim * 4);
     sz += n * 8;
+    if (G.ndeleted > 0) sz += n;  // trailing tombstone bytes
     if (!blob || (int64_t)cap < sz) return sz;
     char* base = (char*)blob;
     char* p = base;
@@ -597,7 +603,8 @@ struct HnswIndex : IndexBase {
     p = base + pad8(p - base);
     memcpy(p, G.data.data(), (size_t)n * dim * 4); p += (size_t)n * dim * 4;
     p = base + pad8(p - base);
-    memcpy(p, G.labels.data(), n * 8);
+    memcpy(p, G.labels.data(), n * 8); p += n * 8;
+    if (G.ndeleted > 0) memcpy(p, G.deleted.data(), (size_t)n);
     return sz;
   }
 };

@@ -63,8 +63,68 @@ const float* IndexBase::prepare_queries(int64_t nq, const float* xq_dev, cudaStr
   return q;
 }
 
-void IndexBase::save(const std::string&) { fail(B200VS_EVECTOR_NOT_SUPPORT, "save not supported for this index type"); }
-void IndexBase::load(const std::string&) { fail(B200VS_EVECTOR_NOT_SUPPORT, "load not supported for this index type"); }
+// Save / Load (VectorIndex::Save/Load, src/vector/vector_index.h:168-170; reference: faiss::write_index / read_index at
+// vector_index_flat.cc:354,:379 and hnswlib saveIndex at vector_index_hnsw.cc:290).  Own container, not faiss-compatible
+// (SURVEY 8f-4): header, trained-state blob, then the live rows in list-major order exactly as stored.
+namespace {
+struct FileHdr { char magic[8]; int32_t type, metric, dim, nlist; int64_t state_len, count; };
+void wr(FILE* f, const void* p, size_t n) { if (n && fwrite(p, 1, n, f) != n) fail(B200VS_EINTERNAL, "short write"); }
+void rd(FILE* f, void* p, size_t n) { if (n && fread(p, 1, n, f) != n) fail(B200VS_EINTERNAL, "short read / truncated index file"); }
+}  // namespace
+
+void IndexBase::save(const std::string& path) {
+  if (type == B200VS_IVF_PQ) fail(B200VS_EVECTOR_NOT_SUPPORT, "save of PQ codes is not implemented");
+  const int64_t st_len = get_state(nullptr, 0);
+  std::vector<unsigned char> st((size_t)std::max<int64_t>(st_len, 0));
+  if (st_len > 0) get_state(st.data(), st.size());
+  const int nl = export_nlist();
+  const int64_t n = type == B200VS_HNSW ? 0 : count();  // the HNSW blob already carries rows + labels
+  std::vector<int64_t> off(nl + 1, 0), ids((size_t)n);
+  std::vector<float> vec((size_t)n * dim);
+  if (n) export_lists(off.data(), vec.data(), nullptr, ids.data());
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) fail(B200VS_EINTERNAL, "cannot open " + path);
+  try {
+    FileHdr h;
+    memcpy(h.magic, "B2VSIDX1", 8);
+    h.type = type; h.metric = metric; h.dim = dim; h.nlist = nl; h.state_len = st_len > 0 ? st_len : 0; h.count = n;
+    wr(f, &h, sizeof(h));
+    wr(f, st.data(), st.size());
+    wr(f, off.data(), off.size() * 8);
+    wr(f, ids.data(), ids.size() * 8);
+    wr(f, vec.data(), vec.size() * 4);
+  } catch (...) { fclose(f); throw; }
+  fclose(f);
+}
+
+void IndexBase::load(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) fail(B200VS_EINTERNAL, "cannot open " + path);
+  try {
+    FileHdr h;
+    rd(f, &h, sizeof(h));
+    if (memcmp(h.magic, "B2VSIDX1", 8) != 0 || h.type != (int)type || h.metric != (int)metric || h.dim != dim)
+      fail(B200VS_EINTERNAL, "index file does not match this index (type / metric / dimension)");
+    if (count() != 0) fail(B200VS_EINTERNAL, "load into a non-empty index");
+    std::vector<unsigned char> st((size_t)h.state_len);
+    rd(f, st.data(), st.size());
+    if (h.state_len > 0) set_state(st.data(), st.size());
+    std::vector<int64_t> off((size_t)h.nlist + 1), ids((size_t)h.count);
+    std::vector<float> vec((size_t)h.count * dim);
+    rd(f, off.data(), off.size() * 8);
+    rd(f, ids.data(), ids.size() * 8);
+    rd(f, vec.data(), vec.size() * 4);
+    loading = true;
+    try {
+      for (int64_t a = 0; a < h.count; a += 32768) {
+        const int64_t m = std::min<int64_t>(32768, h.count - a);
+        add(m, vec.data() + (size_t)a * dim, ids.data() + a, false);
+      }
+    } catch (...) { loading = false; throw; }
+    loading = false;
+  } catch (...) { fclose(f); throw; }
+  fclose(f);
+}
 
 void check_batch_ids_unique(int64_t n, const int64_t* ids) {  // CheckVectorIdDuplicated, vector_index_utils.cc:551-561
   std::unordered_set<int64_t> seen;
@@ -178,7 +238,7 @@ struct FlatIndex : IndexBase {
     B200VS_CUDA(cudaMemcpyAsync(st, x, (size_t)n * dim * 4, cudaMemcpyHostToDevice, stream));
     B200VS_CUDA(cudaMemcpyAsync(st_ids, in_ids, (size_t)n * 8, cudaMemcpyHostToDevice, stream));
     B200VS_CUDA(cudaMemcpyAsync(st_slots, slots.data(), (size_t)n * 8, cudaMemcpyHostToDevice, stream));
-    if (metric == B200VS_COSINE) launch_normalize_faiss(st, n, dim, stream);  // flat.cc:155 (normalize_)
+    if (metric == B200VS_COSINE && !loading) launch_normalize_faiss(st, n, dim, stream);  // flat.cc:155 (normalize_)
     float* st_norms = scratch.alloc<float>(n);
     launch_scatter_rows(st, st_ids, st_slots, n, dim, vecs.p, ids.p, norms.p, st_norms, stream);
     max_norm = std::max(max_norm, device_max_norm(this, st_norms, n, stream));
@@ -303,6 +363,7 @@ struct IvfFlatIndex : IndexBase {
     nlist = p.nlist > 0 ? p.nlist : 2048;  // Constant::kCreateIvfFlatParamNcentroids
   }
   bool is_trained() const override { return trained; }
+  int export_nlist() const override { return nlist; }
 
   void install_centroids(const float* host_c, int k) {
     quiesce();
@@ -454,7 +515,7 @@ void IvfFlatIndex::add(int64_t n, const float* x, const int64_t* in_ids, bool up
   long long* st_slots = scratch.alloc<long long>(n);
   B200VS_CUDA(cudaMemcpyAsync(st, x, (size_t)n * dim * 4, cudaMemcpyHostToDevice, stream));
   B200VS_CUDA(cudaMemcpyAsync(st_ids, in_ids, (size_t)n * 8, cudaMemcpyHostToDevice, stream));
-  if (metric == B200VS_COSINE) launch_normalize_faiss(st, n, dim, stream);
+  if (metric == B200VS_COSINE && !loading) launch_normalize_faiss(st, n, dim, stream);
   assign_dev(st, n, st_list, stream);
   std::vector<long long> h_list(n), slots(n);
   B200VS_CUDA(cudaMemcpyAsync(h_list.data(), st_list, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));

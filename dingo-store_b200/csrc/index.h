@@ -127,6 +127,8 @@ struct IndexBase {
   } scratch{this};
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool profiling = false;  // b200vs_set_profiling: time the dominant scan kernel with CUDA events
+  bool loading = false;    // Load(): rows come back exactly as stored (already normalised for cosine)
+  virtual int export_nlist() const { return 1; }
 
   IndexBase(b200vs_type t, b200vs_metric m, int d, const b200vs_params& p);
   virtual ~IndexBase();

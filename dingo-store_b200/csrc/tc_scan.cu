@@ -421,6 +421,8 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // per-query capture threshold: the k-th smallest sampled score (an upper bound of the k-th smallest score overall)
 // ---------------------------------------------------------------------------------------------
+__device__ uint32_t block_kth_key(const unsigned long long* keys, int n, int k);
+
 constexpr int TAU_PL = 4096;  // (sample slot, column) pairs staged per query
 constexpr int TAU_SORT = 4096;  // sampled scores sorted in one shot when they fit
 
@@ -454,27 +456,20 @@ tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos,
   const int np_all = s_np;
   const int np = min(np_all, TAU_PL);
   const int tot = np * TC_SAMPLE;
-  if (np_all <= TAU_PL && tot <= TAU_SORT) {  // common case: sort all sampled scores once (bitonic, shared memory)
-    float* vals = reinterpret_cast<float*>(smem + (size_t)TAU_PL * 8);
-    int m = 32;
-    while (m < tot) m <<= 1;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
-      float v = TC_INF;
-      if (i < tot) { const int2 pr = s_pairs[i / TC_SAMPLE]; v = sample[((size_t)pr.x * TC_NQT + pr.y) * TC_SAMPLE + (i % TC_SAMPLE)]; }
-      vals[i] = v;
+  if (np_all <= TAU_PL && tot <= TAU_SORT) {  // common case: radix-select the k-th smallest sampled score in shared memory
+    unsigned long long* vals = reinterpret_cast<unsigned long long*>(smem + (size_t)TAU_PL * 8);
+    __shared__ int s_fin;
+    if (threadIdx.x == 0) s_fin = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+      const int2 pr = s_pairs[i / TC_SAMPLE];
+      const float v = sample[((size_t)pr.x * TC_NQT + pr.y) * TC_SAMPLE + (i % TC_SAMPLE)];
+      if (v < TC_INF) vals[atomicAdd(&s_fin, 1)] = (unsigned long long)f2ord(v) << 32;
     }
     __syncthreads();
-    for (int size = 2; size <= m; size <<= 1)
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int i = threadIdx.x; i < (m >> 1); i += blockDim.x) {
-          const int pos = 2 * i - (i & (stride - 1)), j = pos + stride;
-          const bool up = (pos & size) == 0;
-          const float a = vals[pos], b = vals[j];
-          if (up ? b < a : a < b) { vals[pos] = b; vals[j] = a; }
-        }
-        __syncthreads();
-      }
-    if (threadIdx.x == 0) tau[q] = k <= tot ? vals[k - 1] : TC_INF;  // +inf entries (masked rows) sort last
+    const int nfin = s_fin;
+    const uint32_t kth = nfin >= k ? block_kth_key(vals, nfin, k) : 0u;
+    if (threadIdx.x == 0) tau[q] = nfin >= k ? ord2f(kth) : TC_INF;
     return;
   }
   for (int base = 0; base < tot; base += blockDim.x) {
@@ -502,10 +497,11 @@ constexpr int FIN_SEG = 2048;  // in-window rows staged per round
 
 __device__ __forceinline__ float tc_eps(bool l2, float qnorm_sq, float max_norm, int d, bool split) {
   // rigorous bound on |approx score - exact score|.  Operand term: single-pass TF32 = rows truncated
-  // (<= 2^-10 relative) + query rounded (<= 2^-11) -> 2^-9 with slack; split pass (hi*hi + lo*hi + hi*lo) -> 2^-19.
+  // (< 2^-10 relative) + query rounded to nearest (<= 2^-11) = 1.5 * 2^-10 (the 2^-21 cross term and the FP32 accumulation
+  // are covered by the second summand); split pass (hi*hi + lo*hi + hi*lo) -> 2^-19.
   // Accumulation term: FP32 sums of d terms on both sides (tensor core, norms, and the exact kernel itself).
   const float qn = sqrtf(qnorm_sq);
-  const float operand = (l2 ? 2.f : 1.f) * (split ? 1.9073486e-6f /*2^-19*/ : 0.001953125f /*2^-9*/) * qn * max_norm;
+  const float operand = (l2 ? 2.f : 1.f) * (split ? 1.9073486e-6f /*2^-19*/ : 0.0014648438f /*2^-10 + 2^-11*/) * qn * max_norm;
   const float accum = 2.f * (float)(d + 64) * 5.9604645e-8f /*2^-24*/ * (l2 ? max_norm * max_norm + 2.f * qn * max_norm : qn * max_norm);
   return operand + accum;
 }
@@ -1058,7 +1054,7 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   // 1) sample pass -> per-query capture thresholds
   p.mode = 0; p.work_counter = P.work;
   tc_launch(P, p, P.sbound, s);
-  tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, (size_t)TAU_PL * 8 + std::max(sel_smem, (size_t)TAU_SORT * 4), s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, k, pool, tau);
+  tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, (size_t)TAU_PL * 8 + std::max(sel_smem, (size_t)TAU_SORT * 8), s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, k, pool, tau);
   // 2) capture pass: stream every probed list chunk once, keep rows under the threshold
   p.mode = 1; p.work_counter = P.work + 1;
   {
@@ -1069,8 +1065,8 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   // 3) window select + exact rerank + certification
   const size_t fast_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_MAXW * 16 + (size_t)cap * 8;
   if (fast_smem <= 200 * 1024) {  // one 64-bit sort of the captured rows + a small exact sort
-    if (l2) tc_final_fast_kernel<true><<<(unsigned)nq, FIN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
-    else tc_final_fast_kernel<false><<<(unsigned)nq, FIN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
+    if (l2) tc_final_fast_kernel<true><<<(unsigned)nq, SCAN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
+    else tc_final_fast_kernel<false><<<(unsigned)nq, SCAN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
   } else {
     const size_t fin_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + sel_smem;
     if (l2) tc_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags);
