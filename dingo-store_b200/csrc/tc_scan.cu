@@ -502,7 +502,7 @@ __device__ __forceinline__ float tc_eps(bool l2, float qnorm_sq, float max_norm,
   // Accumulation term: FP32 sums of d terms on both sides (tensor core, norms, and the exact kernel itself).
   const float qn = sqrtf(qnorm_sq);
   const float operand = (l2 ? 2.f : 1.f) * (split ? 1.9073486e-6f /*2^-19*/ : 0.0014648438f /*2^-10 + 2^-11*/) * qn * max_norm;
-  const float accum = 2.f * (float)(d + 64) * 5.9604645e-8f /*2^-24*/ * (l2 ? max_norm * max_norm + 2.f * qn * max_norm : qn * max_norm);
+  const float accum = 2.f * (float)(d + 64) * 5.9604645e-8f /*2^-24*/ * (l2 ? (max_norm + qn) * (max_norm + qn) : qn * max_norm);
   return operand + accum;
 }
 
