@@ -174,7 +174,7 @@ def workload_config(args, world):
                         f"batch={args.batch} per GPU, top-{args.k} (BASELINE configs[1] at the metric's batch 1024)",
             "index": "IVF_FLAT", "metric_type": "L2", "nb_per_gpu": args.nb, "dim": args.dim, "nlist_per_gpu": args.nlist,
             "nprobe": args.nprobe, "batch_per_gpu": args.batch, "topk": args.k, "batches_in_flight": args.in_flight,
-            "parallelism": f"list-sharded x{world}, 1 all_gather + merge" if world > 1 else "single GPU",
+            "parallelism": f"list-sharded x{world}: sharded coarse quantiser (all_gather of per-rank top-nprobe) + list scan + all_gather of per-shard top-k, merge kernels" if world > 1 else "single GPU",
             "l2_flush": "inputs larger than L2: every step streams the probed lists (~3.1 GB per GPU >> 126 MB L2)"}
 
 
@@ -266,18 +266,39 @@ def main():
 
     launches = [0]
 
+    if world > 1:  # sharded coarse quantiser: each rank ranks its own centroid rows, one small all-gather, merge
+        np_ = args.nprobe
+        c_s = torch.empty((nq, np_), dtype=torch.float32, device=dev)
+        c_l = torch.empty((nq, np_), dtype=torch.int64, device=dev)
+        gc_s = torch.empty((world, nq, np_), dtype=torch.float32, device=dev)
+        gc_l = torch.empty((world, nq, np_), dtype=torch.int64, device=dev)
+        p_s = torch.empty((nq, np_), dtype=torch.float32, device=dev)
+        p_l = torch.empty((nq, np_), dtype=torch.int64, device=dev)
+
+    def sharded_search(q_ptr, ln, st):
+        """list-sharded batch: local coarse -> all-gather -> merged probes -> local list scan -> all-gather -> merged top-k"""
+        ix.coarse_device(nq, q_ptr, np_, rank * nlist_local, (rank + 1) * nlist_local, c_s.data_ptr(), c_l.data_ptr(), stream=st.cuda_stream)
+        with torch.cuda.stream(st):
+            dist.all_gather_into_tensor(gc_s.view(-1), c_s.view(-1))
+            dist.all_gather_into_tensor(gc_l.view(-1), c_l.view(-1))
+        b200vs.merge_topk_device(local_rank, world, nq, np_, gc_s.data_ptr(), gc_l.data_ptr(), p_s.data_ptr(), p_l.data_ptr(), st.cuda_stream)
+        ix.search_probes_device(nq, q_ptr, k, p_l.data_ptr(), np_, out_d[ln].data_ptr(), out_i[ln].data_ptr(), stream=st.cuda_stream, sp=sp)
+        launches[0] += ix.stats()[0] + 6
+        with torch.cuda.stream(st):
+            dist.all_gather_into_tensor(g_d[ln].view(-1), out_d[ln].view(-1))
+            dist.all_gather_into_tensor(g_i[ln].view(-1), out_i[ln].view(-1))
+        b200vs.merge_topk_device(local_rank, world, nq, k, g_d[ln].data_ptr(), g_i[ln].data_ptr(), m_d[ln].data_ptr(), m_i[ln].data_ptr(), st.cuda_stream)
+        launches[0] += 1
+
     def step_device(i, lanes=L):
         ln = i % lanes
         st = streams[ln]
         q = q_dev[i % nbatches]
+        if world > 1:
+            sharded_search(q.data_ptr(), ln, st)
+            return
         ix.search_device(nq, q.data_ptr(), k, out_d[ln].data_ptr(), out_i[ln].data_ptr(), stream=st.cuda_stream, sp=sp)
         launches[0] += ix.stats()[0]
-        if world > 1:
-            with torch.cuda.stream(st):
-                dist.all_gather_into_tensor(g_d[ln].view(-1), out_d[ln].view(-1))
-                dist.all_gather_into_tensor(g_i[ln].view(-1), out_i[ln].view(-1))
-            b200vs.merge_topk_device(local_rank, world, nq, k, g_d[ln].data_ptr(), g_i[ln].data_ptr(), m_d[ln].data_ptr(), m_i[ln].data_ptr(), st.cuda_stream)
-            launches[0] += 1
 
     def timed_device(steps, lanes):
         """K steps on `lanes` streams; CUDA events on main_stream bracket all of them."""
@@ -332,10 +353,8 @@ def main():
         st = streams[ln]
         with torch.cuda.stream(st):
             qd = q.to(dev, non_blocking=True)
-            ix.search_device(nq, qd.data_ptr(), k, out_d[ln].data_ptr(), out_i[ln].data_ptr(), stream=st.cuda_stream, sp=sp)
-            dist.all_gather_into_tensor(g_d[ln].view(-1), out_d[ln].view(-1))
-            dist.all_gather_into_tensor(g_i[ln].view(-1), out_i[ln].view(-1))
-            b200vs.merge_topk_device(local_rank, world, nq, k, g_d[ln].data_ptr(), g_i[ln].data_ptr(), m_d[ln].data_ptr(), m_i[ln].data_ptr(), st.cuda_stream)
+        sharded_search(qd.data_ptr(), ln, st)
+        with torch.cuda.stream(st):
             hd[ln].copy_(m_d[ln], non_blocking=True)
             hi[ln].copy_(m_i[ln], non_blocking=True)
         st.synchronize()
@@ -377,7 +396,10 @@ def main():
     ix.set_profiling(True)
     kt, rows = [], 0
     for i in range(3):
-        ix.search_device(nq, q_dev[i % nbatches].data_ptr(), k, out_d[0].data_ptr(), out_i[0].data_ptr(), stream=stream.cuda_stream, sp=sp)
+        if world > 1:
+            sharded_search(q_dev[i % nbatches].data_ptr(), 0, stream)
+        else:
+            ix.search_device(nq, q_dev[i % nbatches].data_ptr(), k, out_d[0].data_ptr(), out_i[0].data_ptr(), stream=stream.cuda_stream, sp=sp)
         torch.cuda.synchronize()
         st = ix.stats()
         kt.append(st[3] / 1e9)

@@ -168,6 +168,36 @@ int b200vs_search_device(b200vs_index* h, int64_t nq, const float* xq_dev, int32
   });
 }
 
+int b200vs_coarse_device(b200vs_index* h, int64_t nq, const float* xq_dev, int32_t nprobe, int32_t list_begin, int32_t list_end,
+                         float* out_score_dev, int64_t* out_lists_dev, void* stream) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    if (nq <= 0 || !xq_dev || !out_score_dev || !out_lists_dev) fail(B200VS_EILLEGAL_PARAMETERS, "bad coarse arguments");
+    std::shared_lock<std::shared_mutex> rl(ix->rw);
+    ix->set_device();
+    LaneGuard lane(ix, (cudaStream_t)stream);
+    ix->coarse_range_dev(nq, xq_dev, nprobe, list_begin, list_end, out_score_dev, (long long*)out_lists_dev, lane.stream);
+    return B200VS_OK;
+  });
+}
+
+int b200vs_search_probes_device(b200vs_index* h, int64_t nq, const float* xq_dev, int32_t k, const int64_t* probes_dev, int32_t nprobe,
+                                const b200vs_search_params* sp, float* out_dist_dev, int64_t* out_ids_dev, void* stream) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    check_search_args(ix, nq, xq_dev, sp);
+    if (k <= 0) return B200VS_OK;
+    if (!probes_dev || nprobe <= 0 || !out_ids_dev) fail(B200VS_EILLEGAL_PARAMETERS, "bad probe arguments");
+    std::shared_lock<std::shared_mutex> rl(ix->rw);
+    ix->set_device();
+    LaneGuard lane(ix, (cudaStream_t)stream);
+    for (int i = 0; i < 8; ++i) ix->stats[i] = 0;
+    SearchCtx sc = make_ctx(ix, sp, lane.stream);
+    ix->search_probes_dev(nq, xq_dev, k, (const long long*)probes_dev, nprobe, sc, out_dist_dev, (long long*)out_ids_dev, lane.stream);
+    return B200VS_OK;
+  });
+}
+
 int b200vs_search(b200vs_index* h, int64_t nq, const float* xq, int32_t k, const b200vs_search_params* sp, float* out_dist,
                   int64_t* out_ids) {
   return guarded([&]() -> int {

@@ -443,6 +443,9 @@ struct IvfFlatIndex : IndexBase {
   void search_dev(int64_t nq, const float* xq, int k, const SearchCtx& sc, float* od, long long* oi, cudaStream_t s) override;
   void range_search_dev(int64_t nq, const float* xq, float radius, int max_results, const SearchCtx& sc, float* od,
                         long long* oi, int* oc, cudaStream_t s) override;
+  void coarse_range_dev(int64_t nq, const float* xq, int nprobe, int c0, int c1, float* out_score, long long* out_lists, cudaStream_t s) override;
+  void search_probes_dev(int64_t nq, const float* xq, int k, const long long* probes, int nprobe, const SearchCtx& sc, float* od,
+                         long long* oi, cudaStream_t s) override;
 
   long long* coarse(int64_t nq, const float* q, int nprobe, cudaStream_t s, bool allow_tc = true) {
     if (allow_tc && tc_coarse_eligible(this, nq, nlist, nprobe)) {  // dense TF32 scores + certified exact re-score
@@ -601,6 +604,41 @@ void IvfFlatIndex::search_dev(int64_t nq, const float* xq, int k, const SearchCt
   const float* q = prepare_queries(nq, xq, s);
   const int nprobe = resolve_nprobe(sc);
   long long* probes = coarse(nq, q, nprobe, s, !sc.exact_only);
+  if (profiling) profile_probed(this, probes, nq * nprobe, nlist, L.d_len.p, s);
+  const TcView v = view();
+  if (L.live > 0 && tc_eligible(this, v, nq, k, nprobe, sc)) {
+    tc_search(this, v, metric == B200VS_L2, nq, q, k, probes, nprobe, sc, od, oi, s);
+    return;
+  }
+  ScanJob j = list_job(sc, probes, nprobe);
+  j.dominant = true;
+  run_scan(this, j, nq, q, k, od, nullptr, oi, nullptr, s);
+}
+
+void IvfFlatIndex::coarse_range_dev(int64_t nq, const float* xq, int nprobe, int c0, int c1, float* out_score, long long* out_lists, cudaStream_t s) {
+  if (!trained) fail(B200VS_EVECTOR_NOT_TRAIN, "not train");
+  if (c0 < 0 || c1 > nlist || c0 >= c1 || nprobe <= 0 || nprobe > c1 - c0) fail(B200VS_EILLEGAL_PARAMETERS, "bad centroid range / nprobe");
+  const float* q = prepare_queries(nq, xq, s);
+  const int rows = c1 - c0;
+  if (tc_coarse_eligible(this, nq, rows, nprobe)) {
+    TcView v = cent_view();
+    v.vecs += (size_t)c0 * dim; v.vecs_hi += (size_t)c0 * dim; v.vecs_lo += (size_t)c0 * dim; v.ids += c0; v.norms += c0;
+    v.arena_rows = rows; v.total_chunks = (rows + TC_CHUNK - 1) / TC_CHUNK; v.max_chunks_per_list = (int)v.total_chunks;
+    v.id_offset = c0; v.api_scores = true;
+    tc_coarse(this, v, metric == B200VS_L2, nq, q, nprobe, out_lists, out_score, s);
+    return;
+  }
+  ScanJob j;
+  j.l2 = metric == B200VS_L2;
+  j.vecs = centroids.p + (size_t)c0 * dim; j.ids = cent_ids.p + c0; j.d = dim; j.mode = 0; j.n = rows;
+  run_scan(this, j, nq, q, nprobe, nullptr, out_score, out_lists, nullptr, s);  // raw metric value
+  if (metric != B200VS_L2) launch_negate(out_score, nq * nprobe, s);             // -> ascending ranking score
+}
+
+void IvfFlatIndex::search_probes_dev(int64_t nq, const float* xq, int k, const long long* probes, int nprobe, const SearchCtx& sc, float* od,
+                                     long long* oi, cudaStream_t s) {
+  if (!trained) { fill_empty_results(nq, k, od, oi, s); return; }
+  const float* q = prepare_queries(nq, xq, s);
   if (profiling) profile_probed(this, probes, nq * nprobe, nlist, L.d_len.p, s);
   const TcView v = view();
   if (L.live > 0 && tc_eligible(this, v, nq, k, nprobe, sc)) {

@@ -149,6 +149,17 @@ struct IndexBase {
     (void)nq; (void)xq; (void)radius; (void)max_results; (void)sc; (void)out_dist; (void)out_ids; (void)out_counts; (void)s;
     fail(B200VS_EVECTOR_NOT_SUPPORT, "range search not supported");
   }
+  // list-sharded multi-GPU building blocks (IVF types): coarse quantiser over centroid rows [c0, c1) only, and the list
+  // scan for caller-supplied (merged) probes
+  virtual void coarse_range_dev(int64_t nq, const float* xq, int nprobe, int c0, int c1, float* out_score, long long* out_lists, cudaStream_t s) {
+    (void)nq; (void)xq; (void)nprobe; (void)c0; (void)c1; (void)out_score; (void)out_lists; (void)s;
+    fail(B200VS_EVECTOR_NOT_SUPPORT, "coarse quantiser only exists for IVF_FLAT");
+  }
+  virtual void search_probes_dev(int64_t nq, const float* xq, int k, const long long* probes, int nprobe, const SearchCtx& sc, float* od,
+                                 long long* oi, cudaStream_t s) {
+    (void)nq; (void)xq; (void)k; (void)probes; (void)nprobe; (void)sc; (void)od; (void)oi; (void)s;
+    fail(B200VS_EVECTOR_NOT_SUPPORT, "probe-driven search only exists for IVF_FLAT");
+  }
   virtual int64_t count() const = 0;
   virtual int64_t deleted_count() const { return 0; }
   virtual int64_t memory_size() const = 0;
@@ -225,6 +236,7 @@ void launch_move_rows(const float* svecs, const long long* sids, const float* sn
                       cudaStream_t s);
 void launch_set_ids(long long* ids, const long long* slots, int64_t n, long long value, cudaStream_t s);
 void launch_iota(long long* p, int64_t n, cudaStream_t s);
+void launch_negate(float* p, int64_t n, cudaStream_t s);
 void launch_merge_api(int nparts, int64_t nq, int k, const float* pd, const long long* pi, float* od, long long* oi,
                       cudaStream_t s);
 

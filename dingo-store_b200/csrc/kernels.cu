@@ -136,6 +136,14 @@ void launch_set_ids(long long* ids, const long long* slots, int64_t n, long long
   set_ids_kernel<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(ids, slots, n, value);
   B200VS_CUDA(cudaGetLastError());
 }
+static __global__ void negate_kernel(float* p, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = -p[i];
+}
+void launch_negate(float* p, int64_t n, cudaStream_t s) {
+  if (n > 0) negate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n);
+}
+
 void launch_iota(long long* p, int64_t n, cudaStream_t s) {
   if (n <= 0) return;
   iota_kernel<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(p, n);

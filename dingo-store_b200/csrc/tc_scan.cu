@@ -676,7 +676,7 @@ template <bool L2>
 static __global__ void __launch_bounds__(SCAN_THREADS)
 tc_coarse_final_fast_kernel(const float* __restrict__ dense, long long ld, int nrows, const float* __restrict__ qnorm, float max_norm,
                             const float* __restrict__ q, const float* __restrict__ vecs, int d, int k, int maxw,
-                            long long* out_probes, float* out_raw) {
+                            long long id_offset, int api_scores, long long* out_probes, float* out_raw) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_m;
   const int qi = blockIdx.x;
@@ -694,8 +694,12 @@ tc_coarse_final_fast_kernel(const float* __restrict__ dense, long long ld, int n
   const float two_eps = 2.f * tc_eps(L2, qnorm[qi], max_norm, d, true);
   const int have = window_select<L2, true>(keys, nrows, k, two_eps, qs, vecs, nullptr, d, ex_kd, ex_id, rows, maxw, &fits, &a_k, &s_m);
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    out_probes[(size_t)qi * k + i] = i < have ? ex_id[i] : -1;
-    if (out_raw) { const float v = i < have ? ord2f(ex_kd[i]) : 0.f; out_raw[(size_t)qi * k + i] = L2 ? v : -v; }
+    out_probes[(size_t)qi * k + i] = i < have ? ex_id[i] + id_offset : -1;
+    if (out_raw) {
+      const float v = i < have ? ord2f(ex_kd[i]) : 0.f;
+      const float raw = L2 ? v : -v;
+      out_raw[(size_t)qi * k + i] = api_scores ? v : raw;  // api_scores: the ranking score itself (L2 distance | -ip), ascending
+    }
   }
 }
 
@@ -786,7 +790,7 @@ template <bool L2>
 static __global__ void __launch_bounds__(SCAN_THREADS)
 tc_coarse_final_kernel(const float* __restrict__ dense, long long ld, int nrows, const float* __restrict__ qnorm, float max_norm,
                        const float* __restrict__ q, const float* __restrict__ vecs, int d, int k, int pool_cap,
-                       long long* out_probes, float* out_raw) {
+                       long long id_offset, int api_scores, long long* out_probes, float* out_raw) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_m;
   const int qi = blockIdx.x;
@@ -837,8 +841,12 @@ tc_coarse_final_kernel(const float* __restrict__ dense, long long ld, int nrows,
   sel.prune();
   const int have = *sel.count;
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    out_probes[(size_t)qi * k + i] = i < have ? sel.kid[i] : -1;
-    if (out_raw) { const float v = i < have ? ord2f(sel.kd[i]) : 0.f; out_raw[(size_t)qi * k + i] = L2 ? v : -v; }
+    out_probes[(size_t)qi * k + i] = i < have ? sel.kid[i] + id_offset : -1;
+    if (out_raw) {
+      const float v = i < have ? ord2f(sel.kd[i]) : 0.f;
+      const float raw = L2 ? v : -v;
+      out_raw[(size_t)qi * k + i] = api_scores ? v : raw;  // api_scores: the ranking score itself (L2 distance | -ip), ascending
+    }
   }
 }
 
@@ -1133,13 +1141,13 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   if (nrows <= COARSE_FAST && nprobe <= nrows) {
     const int maxw = std::max(2, next_pow2(nrows));
     const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)maxw * 24;
-    if (l2) tc_coarse_final_fast_kernel<true><<<(unsigned)nq, FIN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, out_probes, out_raw);
-    else tc_coarse_final_fast_kernel<false><<<(unsigned)nq, FIN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, out_probes, out_raw);
+    if (l2) tc_coarse_final_fast_kernel<true><<<(unsigned)nq, FIN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw);
+    else tc_coarse_final_fast_kernel<false><<<(unsigned)nq, FIN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw);
   } else {
     const int pool = select_pool_cap(nprobe, SCAN_THREADS);
     const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + BlockSelect::smem_bytes(pool);
-    if (l2) tc_coarse_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
-    else tc_coarse_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, out_probes, out_raw);
+    if (l2) tc_coarse_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw);
+    else tc_coarse_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw);
   }
   B200VS_CUDA(cudaGetLastError());
   ix->launch_count(4);

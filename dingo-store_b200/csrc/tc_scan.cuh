@@ -84,6 +84,8 @@ struct TcView {
   const float* vecs_hi = nullptr;  // optional split of the rows for the error-compensated coarse pass:
   const float* vecs_lo = nullptr;  //   hi = x with the low 13 mantissa bits cleared, lo = x - hi (both exact)
   bool flat = false;         // single list covering rows [0, arena_rows)
+  long long id_offset = 0;   // tc_coarse on a slice of the centroid table: added to the returned row indices
+  bool api_scores = false;   // tc_coarse: return the ascending ranking score (L2 distance | -ip) instead of the raw metric value
 };
 
 // true when this search can use the tensor-core pass (otherwise the caller runs the exact scan)

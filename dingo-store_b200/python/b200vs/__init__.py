@@ -20,7 +20,7 @@ OK, EILLEGAL_PARAMETERS, EVECTOR_INVALID, EVECTOR_NOT_TRAIN, EVECTOR_NOT_SUPPORT
 # every symbol include/b200vs.h declares (checked by tests/test_abi.py without a GPU)
 ABI_SYMBOLS = [
     "b200vs_create", "b200vs_destroy", "b200vs_train", "b200vs_set_trained_state", "b200vs_get_trained_state",
-    "b200vs_add_with_ids", "b200vs_remove_ids", "b200vs_search", "b200vs_search_device", "b200vs_range_search",
+    "b200vs_add_with_ids", "b200vs_remove_ids", "b200vs_search", "b200vs_search_device", "b200vs_coarse_device", "b200vs_search_probes_device", "b200vs_range_search",
     "b200vs_count", "b200vs_deleted_count", "b200vs_memory_size", "b200vs_is_trained", "b200vs_dimension",
     "b200vs_save", "b200vs_load", "b200vs_export_lists", "b200vs_merge_topk_device", "b200vs_last_search_stats", "b200vs_set_profiling",
     "b200vs_last_error", "b200vs_version",
@@ -71,6 +71,8 @@ def lib():
     L.b200vs_remove_ids.argtypes = [vp, i64, vp, ctypes.POINTER(i64)]
     L.b200vs_search.argtypes = [vp, i64, vp, i32, ctypes.POINTER(SearchParams), vp, vp]
     L.b200vs_search_device.argtypes = [vp, i64, vp, i32, ctypes.POINTER(SearchParams), vp, vp, vp]
+    L.b200vs_coarse_device.argtypes = [vp, i64, vp, i32, i32, i32, vp, vp, vp]
+    L.b200vs_search_probes_device.argtypes = [vp, i64, vp, i32, vp, i32, ctypes.POINTER(SearchParams), vp, vp, vp]
     L.b200vs_range_search.argtypes = [vp, i64, vp, f32, i32, ctypes.POINTER(SearchParams), vp, vp, vp]
     L.b200vs_count.argtypes = [vp, ctypes.POINTER(i64)]
     L.b200vs_deleted_count.argtypes = [vp, ctypes.POINTER(i64)]
@@ -192,6 +194,13 @@ class Index:
     def search_device(self, nq, xq_dev_ptr, k, out_dist_dev_ptr, out_ids_dev_ptr, stream=None, sp=None):
         _check(self.L.b200vs_search_device(self.h, nq, xq_dev_ptr, k, ctypes.byref(sp) if sp is not None else None,
                                            out_dist_dev_ptr, out_ids_dev_ptr, stream))
+
+    def coarse_device(self, nq, xq_dev_ptr, nprobe, list_begin, list_end, out_score_dev_ptr, out_lists_dev_ptr, stream=None):
+        _check(self.L.b200vs_coarse_device(self.h, nq, xq_dev_ptr, nprobe, list_begin, list_end, out_score_dev_ptr, out_lists_dev_ptr, stream))
+
+    def search_probes_device(self, nq, xq_dev_ptr, k, probes_dev_ptr, nprobe, out_dist_dev_ptr, out_ids_dev_ptr, stream=None, sp=None):
+        _check(self.L.b200vs_search_probes_device(self.h, nq, xq_dev_ptr, k, probes_dev_ptr, nprobe, ctypes.byref(sp) if sp is not None else None,
+                                                  out_dist_dev_ptr, out_ids_dev_ptr, stream))
 
     def range_search(self, xq, radius, max_results=1024, **kw):
         xq = _f32(xq)

@@ -131,6 +131,18 @@ int b200vs_export_lists(b200vs_index* idx, int64_t* list_off /*[nlist+1]*/, floa
 int b200vs_merge_topk_device(int32_t device, int32_t nparts, int64_t nq, int32_t k, const float* parts_dist,
                              const int64_t* parts_ids, float* out_dist, int64_t* out_ids, void* stream);
 
+/* List-sharded multi-GPU building blocks (IVF_FLAT): every rank holds all centroids but owns only some lists.
+ * b200vs_coarse_device ranks the centroid rows [list_begin, list_end) only (this rank's share of the coarse work):
+ * out_lists = GLOBAL list ids, out_score = the ranking score (L2 distance, or -ip: exact and ascending, so no
+ * rounding can reorder ties), both [nq, nprobe] in (score, list id) order, so the per-rank
+ * results can be all-gathered and merged with b200vs_merge_topk_device into the global top-nprobe
+ * (= faiss quantizer->search(nq, x, nprobe), vector_index_ivf_flat.cc:247-251).  b200vs_search_probes_device then scans
+ * the probed lists this rank owns for those (caller-supplied) probes. */
+int b200vs_coarse_device(b200vs_index* idx, int64_t nq, const float* xq_dev, int32_t nprobe, int32_t list_begin, int32_t list_end,
+                         float* out_score_dev, int64_t* out_lists_dev, void* stream);
+int b200vs_search_probes_device(b200vs_index* idx, int64_t nq, const float* xq_dev, int32_t k, const int64_t* probes_dev, int32_t nprobe,
+                                const b200vs_search_params* sp, float* out_dist_dev, int64_t* out_ids_dev, void* stream);
+
 /* Counters of the last search on this index: [0] kernels launched, [1] queries served by the tensor-core
  * candidate pass, [2] queries that failed certification and were re-run on the exact path; with profiling on
  * (b200vs_set_profiling) also [3] device time of the dominant list-scan kernel in ns (CUDA events on the launch
