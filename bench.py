@@ -404,6 +404,7 @@ def main():
         st = ix.stats()
         kt.append(st[3] / 1e9)
         rows = st[4]
+    prof_stats = list(st)
     ix.set_profiling(False)
     peak, how = measured_peaks()
     kern_s = float(np.mean(kt)) if kt and min(kt) > 0 else None
@@ -450,7 +451,7 @@ def main():
                 "single_stream": {"value": nq * args.steps / (ms_single / 1e3), "unit": "queries/s", "ms_per_step": ms_single / args.steps,
                                   "note": "same K steps strictly back to back on one stream"},
                 "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "recall_at_10_vs_oracle": recall_vs_oracle, "build_seconds": build_s, "search_stats": ix.stats()}
+                "recall_at_10_vs_oracle": recall_vs_oracle, "build_seconds": build_s, "search_stats": ix.stats(), "profile_stats": prof_stats}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -164,6 +164,7 @@ int b200vs_search_device(b200vs_index* h, int64_t nq, const float* xq_dev, int32
     for (int i = 0; i < 8; ++i) ix->stats[i] = 0;
     SearchCtx sc = make_ctx(ix, sp, s);
     ix->search_dev(nq, xq_dev, k, sc, out_dist_dev, (long long*)out_ids_dev, s);
+    if (!stream) B200VS_CUDA(cudaStreamSynchronize(s));  // NULL stream: library-owned stream, results ready on return
     return B200VS_OK;
   });
 }
@@ -177,6 +178,7 @@ int b200vs_coarse_device(b200vs_index* h, int64_t nq, const float* xq_dev, int32
     ix->set_device();
     LaneGuard lane(ix, (cudaStream_t)stream);
     ix->coarse_range_dev(nq, xq_dev, nprobe, list_begin, list_end, out_score_dev, (long long*)out_lists_dev, lane.stream);
+    if (!stream) B200VS_CUDA(cudaStreamSynchronize(lane.stream));
     return B200VS_OK;
   });
 }
@@ -194,6 +196,7 @@ int b200vs_search_probes_device(b200vs_index* h, int64_t nq, const float* xq_dev
     for (int i = 0; i < 8; ++i) ix->stats[i] = 0;
     SearchCtx sc = make_ctx(ix, sp, lane.stream);
     ix->search_probes_dev(nq, xq_dev, k, (const long long*)probes_dev, nprobe, sc, out_dist_dev, (long long*)out_ids_dev, lane.stream);
+    if (!stream) B200VS_CUDA(cudaStreamSynchronize(lane.stream));
     return B200VS_OK;
   });
 }

@@ -16,25 +16,59 @@ thread_local Lane* IndexBase::tl_lane = nullptr;
 thread_local IndexBase* IndexBase::tl_owner = nullptr;
 
 LaneGuard::LaneGuard(IndexBase* ix_, cudaStream_t s) : ix(ix_), lane(nullptr), prev_owner(IndexBase::tl_owner), prev_lane(IndexBase::tl_lane), stream(s) {
-  if (s) {  // caller-provided stream: reuse the lane that last ran on it, else take the next one round-robin
-    for (int i = 0; i < kLanes && !lane; ++i) if (ix->lanes[i].last == s) lane = &ix->lanes[i];
-    if (!lane) lane = &ix->lanes[ix->lane_rr.fetch_add(1) % kLanes];
-    lane->mu.lock();
-  } else {  // host-pointer call: first free lane, on that lane's own stream
-    for (int i = 0; i < kLanes && !lane; ++i) if (ix->lanes[i].mu.try_lock()) lane = &ix->lanes[i];
-    if (!lane) { lane = &ix->lanes[ix->lane_rr.fetch_add(1) % kLanes]; lane->mu.lock(); }
-    if (!lane->own) B200VS_CUDA(cudaStreamCreateWithFlags(&lane->own, cudaStreamNonBlocking));
-    stream = lane->own;
+  const bool own = s == nullptr;  // host-pointer / NULL-stream call: runs on the lane's own stream
+  {
+    std::lock_guard<std::mutex> pick(ix->lane_pick_mu);
+    // 1) the lane this stream used last: its scratch is already ordered behind the caller's earlier work
+    if (!own)
+      for (auto& l : ix->lanes)
+        if (l.last.load() == s && l.mu.try_lock()) { lane = &l; break; }
+    // 2) a free lane nobody else's stream is attached to: for host-pointer calls the most recently used such lane
+    //    (its scratch arena is already sized and hot), else an unused one; failing that, steal the least recently used
+    if (!lane) {
+      auto rank = [&](Lane& l) -> unsigned long long {
+        const cudaStream_t last = l.last.load();
+        if (own && last != nullptr && last == l.own) return (1ull << 60) - l.tick;  // warm host-call lane, MRU first
+        if (last == nullptr) return 1ull << 61;                                       // never used
+        return (1ull << 62) + l.tick;                                                 // attached to a stream: LRU
+      };
+      for (auto& l : ix->lanes) {
+        if (!l.mu.try_lock()) continue;
+        if (!lane) lane = &l;
+        else if (rank(l) < rank(*lane)) { lane->mu.unlock(); lane = &l; }
+        else l.mu.unlock();
+      }
+    }
+    if (lane) lane->tick = ++ix->lane_tick;
   }
-  if (lane->last && lane->last != stream) cudaStreamSynchronize(lane->last);
-  lane->last = stream;
-  IndexBase::tl_owner = ix;
-  IndexBase::tl_lane = lane;
-  lane->s.reset(stream);
+  if (!lane) {  // every lane is busy: queue behind one
+    lane = &ix->lanes[ix->lane_rr.fetch_add(1) % kLanes];
+    lane->mu.lock();
+    std::lock_guard<std::mutex> pick(ix->lane_pick_mu);
+    lane->tick = ++ix->lane_tick;
+  }
+  try {
+    if (own) {
+      if (!lane->own) B200VS_CUDA(cudaStreamCreateWithFlags(&lane->own, cudaStreamNonBlocking));
+      stream = lane->own;
+    }
+    if (lane->last.load() != stream && lane->done_valid.load()) B200VS_CUDA(cudaStreamWaitEvent(stream, lane->done, 0));
+    lane->last.store(stream);
+    IndexBase::tl_owner = ix;
+    IndexBase::tl_lane = lane;
+    lane->s.reset(stream);
+  } catch (...) {
+    IndexBase::tl_owner = prev_owner;
+    IndexBase::tl_lane = prev_lane;
+    lane->mu.unlock();
+    throw;
+  }
 }
 LaneGuard::~LaneGuard() {
   IndexBase::tl_owner = prev_owner;
   IndexBase::tl_lane = prev_lane;
+  if (!lane->done) cudaEventCreateWithFlags(&lane->done, cudaEventDisableTiming);
+  if (lane->done && cudaEventRecord(lane->done, stream) == cudaSuccess) lane->done_valid.store(true);
   lane->mu.unlock();
 }
 
@@ -47,7 +81,10 @@ IndexBase::IndexBase(b200vs_type t, b200vs_metric m, int d, const b200vs_params&
 IndexBase::~IndexBase() {
   cudaSetDevice(device);
   if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
-  for (auto& l : lanes) if (l.own) { cudaStreamSynchronize(l.own); cudaStreamDestroy(l.own); }
+  for (auto& l : lanes) {
+    if (l.done) { cudaEventSynchronize(l.done); cudaEventDestroy(l.done); }
+    if (l.own) { cudaStreamSynchronize(l.own); cudaStreamDestroy(l.own); }
+  }
 }
 
 const float* IndexBase::prepare_queries(int64_t nq, const float* xq_dev, cudaStream_t s) {

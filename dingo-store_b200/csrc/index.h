@@ -80,14 +80,18 @@ struct Scratch {
 
 // A lane = one in-flight search: its own scratch arena, serialised by its own mutex, stream-ordered.  Several lanes let
 // concurrent callers (the reference issues searches from a 16-thread pool, src/server/server.cc:868-873) overlap on the
-// GPU: the small kernels of one batch run under the HBM-bound list scan of another.
+// GPU: the small kernels of one batch run under the HBM-bound list scan of another.  A lane that moves to another
+// stream is ordered behind its previous search with an event (device-side wait, the host never blocks).
 struct Lane {
   Scratch s;
   std::mutex mu;
-  cudaStream_t last = nullptr;  // stream of the lane's previous search (switching streams synchronises the old one)
-  cudaStream_t own = nullptr;   // lane-owned stream for host-pointer calls
+  std::atomic<cudaStream_t> last{nullptr};  // stream of the lane's previous search
+  cudaStream_t own = nullptr;               // lane-owned stream for host-pointer / NULL-stream calls
+  cudaEvent_t done = nullptr;               // recorded behind the lane's latest search
+  std::atomic<bool> done_valid{false};
+  unsigned long long tick = 0;              // last use (lane_pick_mu), for least-recently-used hand-out
 };
-constexpr int kLanes = 4;
+constexpr int kLanes = 8;
 
 struct SearchCtx {  // resolved per-search parameters, device filter included
   int nprobe = 0;
@@ -112,12 +116,14 @@ struct IndexBase {
   std::mutex gpu_mu;     // writers / maintenance (they also hold rw exclusively)
   Lane lanes[kLanes];
   std::atomic<unsigned> lane_rr{0};
+  std::mutex lane_pick_mu;
+  unsigned long long lane_tick = 0;
   static thread_local Lane* tl_lane;       // the calling thread's active lane (set by LaneGuard)
   static thread_local IndexBase* tl_owner;
   Lane& cur() { return (tl_owner == this && tl_lane) ? *tl_lane : lanes[0]; }
   // wait for the asynchronous work of every earlier search (device-pointer searches return before the GPU is done);
   // writers call it before touching index memory or the lane-0 scratch
-  void quiesce() { for (auto& l : lanes) if (l.last) cudaStreamSynchronize(l.last); }
+  void quiesce() { for (auto& l : lanes) if (l.done_valid.load()) cudaEventSynchronize(l.done); }
   struct ScratchProxy {  // `ix->scratch.alloc<T>(n)` resolves to the calling thread's lane
     IndexBase* ix;
     template <class T> T* alloc(size_t n) { return ix->cur().s.alloc<T>(n); }

@@ -135,7 +135,7 @@ static __global__ void tc_plan_kernel(const int* __restrict__ cnt, const int* __
       const int vp = __shfl_up_sync(0xffffffffu, wp, o), vi = __shfl_up_sync(0xffffffffu, wi, o);
       if (lane >= o) { wp += vp; wi += vi; }
     }
-    if (lane == 31) { totals[0] = wi; totals[1] = wp; totals[2] = 0; }
+    if (lane == 31) { totals[0] = wi; totals[1] = wp; totals[2] = 0; totals[3] = 0; }
     s_pairs[lane] = wp - tp; s_items[lane] = wi - ti;  // exclusive warp offsets
   }
   __syncthreads();
@@ -190,6 +190,8 @@ static __global__ void tc_items_kernel(const int* __restrict__ cnt, const int* _
       }
       it.pad[0] = it.pad[1] = 0;
       items[base + ch * ng + g] = it;
+      // profiling aid: tensor-core work = 128-row tiles x padded query columns
+      atomicAdd(totals + 3, ((it.row_end - it.row_begin + TC_BM - 1) / TC_BM) * (it.nq <= 16 ? 16 : (it.nq <= 32 ? 32 : (it.nq <= 64 ? 64 : 128))));
     }
 }
 
@@ -221,8 +223,15 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ float s_tau[2][TC_NQT];
   __shared__ int s_q[2][TC_NQT];
   __shared__ int s_brow[TC_NQT];  // producer-private: query rows of the current item (gather4 mode)
+  // capture staging, one buffer per epilogue warp: hits are appended with a shared-memory atomic and written out
+  // (one global atomicAdd per hit, a whole warp of them in flight) when the item ends, so the score loop never
+  // waits on a global round trip
+  __shared__ unsigned long long s_hit_key[4][TC_HITS];
+  __shared__ int s_hit_q[4][TC_HITS];
+  __shared__ int s_hit_n[4];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 4) s_hit_n[threadIdx.x] = 0;
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmA32); prefetch_tmap(&tmB16); prefetch_tmap(&tmB32); prefetch_tmap(&tmB64); prefetch_tmap(&tmB128); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -269,7 +278,17 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int t = 0; t < ntiles; ++t)
           for (int kb = 0; kb < kblocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], p.b_gather ? bytes_g : bytes);
+            // last tile of a list: fetch only the 32-row boxes that hold list rows (the rest of the stage keeps stale
+            // data, whose scores the epilogue masks) instead of streaming up to 127 rows of the neighbouring list
+            const int trows = rows - t * TC_BM;
+            const int nbox = (p.mode == 1 && !p.split && trows <= TC_BM - TC_SAMPLE) ? (trows + TC_SAMPLE - 1) / TC_SAMPLE : 0;
+            const uint32_t saved = nbox ? TC_A_BYTES - (uint32_t)nbox * (TC_SAMPLE * 128) : 0u;
+            mbar_arrive_expect_tx(&full_bar[stage], (p.b_gather ? bytes_g : bytes) - saved);
+            if (nbox) {
+              for (int j = 0; j < nbox; ++j)
+                tma_load_2d(sA + (size_t)stage * TC_A_BYTES + (size_t)j * (TC_SAMPLE * 128), &tmA32, &full_bar[stage], kb * TC_BK,
+                            (int)(base_row + (long long)t * TC_BM + j * TC_SAMPLE), kEvictFirst);
+            } else
             tma_load_2d(sA + (size_t)stage * TC_A_BYTES, ta, &full_bar[stage], kb * TC_BK, (int)(base_row + (long long)t * TC_BM), kEvictFirst);
             if (p.b_gather) {
               uint8_t* bdst = sB + (size_t)stage * TC_B_BYTES;
@@ -394,8 +413,13 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (p.mode == 1) {
                 if (valid && score <= s_tau[buf][n]) {
                   const int q = s_q[buf][n];
-                  const int sl = atomicAdd(p.cand_cnt + q, 1);
-                  if (sl < p.cap) p.cand[(size_t)q * p.cap + sl] = ((unsigned long long)f2ord(score) << 32) | (unsigned long long)(uint32_t)arow;
+                  const unsigned long long key = ((unsigned long long)f2ord(score) << 32) | (unsigned long long)(uint32_t)arow;
+                  const int h = atomicAdd(&s_hit_n[ew], 1);
+                  if (h < TC_HITS) { s_hit_key[ew][h] = key; s_hit_q[ew][h] = q; }
+                  else {  // staging full: write through
+                    const int sl = atomicAdd(p.cand_cnt + q, 1);
+                    if (sl < p.cap) p.cand[(size_t)q * p.cap + sl] = key;
+                  }
                 }
               } else if (p.mode == 0) {
                 if (ew == 0 && t == 0) p.sample[((size_t)I.sample_slot * TC_NQT + n) * TC_SAMPLE + lane] = valid ? score : TC_INF;
@@ -410,6 +434,18 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      if (p.mode == 1) {  // flush this warp's staged hits
+        __syncwarp();
+        const int nh = min(s_hit_n[ew], TC_HITS);
+        for (int i = lane; i < nh; i += 32) {
+          const int q = s_hit_q[ew][i];
+          const int sl = atomicAdd(p.cand_cnt + q, 1);
+          if (sl < p.cap) p.cand[(size_t)q * p.cap + sl] = s_hit_key[ew][i];
+        }
+        __syncwarp();
+        if (lane == 0) s_hit_n[ew] = 0;
+        __syncwarp();
       }
     }
   }
@@ -1095,6 +1131,11 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
     B200VS_CUDA(cudaMemcpyAsync(&h, qcount, 4, cudaMemcpyDeviceToHost, s));
     B200VS_CUDA(cudaStreamSynchronize(s));
     ix->stats[2] = h;
+    int t[4] = {0, 0, 0, 0};
+    B200VS_CUDA(cudaMemcpyAsync(t, P.totals, 16, cudaMemcpyDeviceToHost, s));
+    B200VS_CUDA(cudaStreamSynchronize(s));
+    ix->stats[6] = t[0];  // work items of the capture pass
+    ix->stats[7] = t[3];  // sum over items of (128-row tiles x padded query columns)
   }
 }
 

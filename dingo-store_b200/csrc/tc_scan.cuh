@@ -28,6 +28,7 @@ constexpr int TC_STAGES = 5;      // TMA->MMA ring depth (5 x 32 KB: leaves ~65 
 constexpr int TC_THREADS = 256;   // warp0 TMA + scheduler, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
 constexpr int TC_CHUNK = 512;     // rows per work item (list chunk): fine grain for dynamic load balance
 constexpr int TC_SPAN = 2048;     // one sampled chunk per TC_SPAN rows of a list
+constexpr int TC_HITS = 512;      // captured rows staged per epilogue warp between flushes
 constexpr int TC_SAMPLE = 32;     // sampled rows per span for the threshold estimate
 constexpr int TC_SQ = 4;          // scheduler queue depth (items the producer may run ahead)
 constexpr uint32_t TC_A_BYTES = TC_BM * 128;

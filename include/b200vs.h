@@ -98,7 +98,9 @@ int b200vs_remove_ids(b200vs_index* idx, int64_t n, const int64_t* ids, int64_t*
 int b200vs_search(b200vs_index* idx, int64_t nq, const float* xq, int32_t k, const b200vs_search_params* sp,
                   float* out_dist, int64_t* out_ids);
 /* Same, with xq / out_dist / out_ids DEVICE pointers on the index's device; enqueued on `stream`
- * (a cudaStream_t, NULL = the index's own stream) and NOT synchronised when it returns. */
+ * (a cudaStream_t) and NOT synchronised when it returns.  stream == NULL runs the search on a library-owned stream and
+ * returns only when the results are complete (it does not touch the legacy default stream).  The same holds for
+ * b200vs_coarse_device and b200vs_search_probes_device. */
 int b200vs_search_device(b200vs_index* idx, int64_t nq, const float* xq_dev, int32_t k,
                          const b200vs_search_params* sp, float* out_dist_dev, int64_t* out_ids_dev, void* stream);
 
@@ -146,7 +148,8 @@ int b200vs_search_probes_device(b200vs_index* idx, int64_t nq, const float* xq_d
 /* Counters of the last search on this index: [0] kernels launched, [1] queries served by the tensor-core
  * candidate pass, [2] queries that failed certification and were re-run on the exact path; with profiling on
  * (b200vs_set_profiling) also [3] device time of the dominant list-scan kernel in ns (CUDA events on the launch
- * stream), [4] rows in the distinct probed lists, [5] distinct probed lists.  Profiling synchronises the stream
+ * stream), [4] rows in the distinct probed lists, [5] distinct probed lists, [6] work items of the tile scan,
+ * [7] its tensor-core work (128-row tiles x padded query columns).  Profiling synchronises the stream
  * inside the call: never leave it on in a timed run. */
 int b200vs_last_search_stats(b200vs_index* idx, int64_t stats[8]);
 int b200vs_set_profiling(b200vs_index* idx, int on);

@@ -25,10 +25,14 @@ def _build(metric, n, d, nlist, seed):
     return ix, xb, ids
 
 
-def _sharded(ix, torch, xq, k, nprobe, nlist, parts, sp=None):
+def _sharded(ix, torch, xq, k, nprobe, nlist, parts, sp=None, own_stream=True):
+    """own_stream: everything is enqueued on one caller stream (the deployed shape).  Otherwise stream = NULL: the
+    library runs each call on a stream of its own and returns when the results are complete."""
     nq = xq.shape[0]
     q = torch.from_numpy(xq).cuda()
-    st = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+    ts = torch.cuda.Stream() if own_stream else None
+    st = ts.cuda_stream if own_stream else None
     per = nlist // parts
     gs = torch.empty((parts, nq, nprobe), dtype=torch.float32, device="cuda")
     gl = torch.empty((parts, nq, nprobe), dtype=torch.int64, device="cuda")
@@ -37,6 +41,8 @@ def _sharded(ix, torch, xq, k, nprobe, nlist, parts, sp=None):
     ps = torch.empty((nq, nprobe), dtype=torch.float32, device="cuda")
     pl = torch.empty((nq, nprobe), dtype=torch.int64, device="cuda")
     b200vs.merge_topk_device(0, parts, nq, nprobe, gs.data_ptr(), gl.data_ptr(), ps.data_ptr(), pl.data_ptr(), st)
+    if not own_stream:
+        torch.cuda.synchronize()  # the merge ran on the legacy default stream
     od = torch.empty((nq, k), dtype=torch.float32, device="cuda")
     oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
     ix.search_probes_device(nq, q.data_ptr(), k, pl.data_ptr(), nprobe, od.data_ptr(), oi.data_ptr(), stream=st, sp=sp)
@@ -76,8 +82,8 @@ def test_sharded_coarse_tile_path_large():
     xq = np.random.default_rng(11).random((1024, d), dtype=np.float32)
     wd, wi = ix.search(xq, k, nprobe=nprobe)
     sp, _keep = b200vs.make_search_params(nprobe=nprobe)
-    for parts in (2, 8):
-        od, oi, ps, pl = _sharded(ix, torch, xq, k, nprobe, nlist, parts, sp=sp)
+    for parts, own in ((2, True), (8, True), (4, False)):
+        od, oi, ps, pl = _sharded(ix, torch, xq, k, nprobe, nlist, parts, sp=sp, own_stream=own)
         assert np.array_equal(oi, wi)
         assert np.array_equal(od.view(np.uint32), wd.view(np.uint32))
 
@@ -91,4 +97,4 @@ def test_coarse_device_rejects_bad_range():
     l = torch.empty((2, 4), dtype=torch.int64, device="cuda")
     for a, b, npb in ((-1, 8, 4), (0, 17, 4), (8, 8, 4), (0, 2, 4)):
         with pytest.raises(b200vs.B200VSError):
-            ix.coarse_device(2, q.data_ptr(), npb, a, b, s.data_ptr(), l.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+            ix.coarse_device(2, q.data_ptr(), npb, a, b, s.data_ptr(), l.data_ptr())
