@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--exact-only", action="store_true", help="force the exact FP32 scan path")
     ap.add_argument("--in-flight", type=int, default=2, help="batches in flight (streams / caller threads); the reference serves "
                     "searches from a 16-thread pool, so concurrent batches are the deployed shape")
+    ap.add_argument("--coarse-shard", default="queries", choices=["queries", "lists"], help="multi-GPU: how the coarse quantiser is split")
     return ap.parse_args()
 
 
@@ -174,7 +175,7 @@ def workload_config(args, world):
                         f"batch={args.batch} per GPU, top-{args.k} (BASELINE configs[1] at the metric's batch 1024)",
             "index": "IVF_FLAT", "metric_type": "L2", "nb_per_gpu": args.nb, "dim": args.dim, "nlist_per_gpu": args.nlist,
             "nprobe": args.nprobe, "batch_per_gpu": args.batch, "topk": args.k, "batches_in_flight": args.in_flight,
-            "parallelism": f"list-sharded x{world}: sharded coarse quantiser (all_gather of per-rank top-nprobe) + list scan + all_gather of per-shard top-k, merge kernels" if world > 1 else "single GPU",
+            "parallelism": f"list-sharded x{world}: coarse quantiser split by {args.coarse_shard} (all_gather of the probe table), list scan of the owned lists, all_gather of per-shard top-k + merge kernel" if world > 1 else "single GPU",
             "l2_flush": "inputs larger than L2: every step streams the probed lists (~3.1 GB per GPU >> 126 MB L2)"}
 
 
@@ -266,24 +267,38 @@ def main():
 
     launches = [0]
 
-    if world > 1:  # sharded coarse quantiser: each rank ranks its own centroid rows, one small all-gather, merge
+    if world > 1:
+        # coarse quantiser of a list-sharded index.  Centroids are replicated, so the coarse work can be split either way:
+        #   queries : rank r ranks ITS slice of the batch against all centroids, one all-gather of the probe table
+        #   lists   : every rank ranks all queries against its own centroid rows, all-gather + merge of the top-nprobe
+        # Both produce the same probe table (tests/test_gpu_sharded_coarse.py); "queries" re-scores each query once.
         np_ = args.nprobe
+        bq = args.batch
         c_s = torch.empty((nq, np_), dtype=torch.float32, device=dev)
         c_l = torch.empty((nq, np_), dtype=torch.int64, device=dev)
-        gc_s = torch.empty((world, nq, np_), dtype=torch.float32, device=dev)
-        gc_l = torch.empty((world, nq, np_), dtype=torch.int64, device=dev)
-        p_s = torch.empty((nq, np_), dtype=torch.float32, device=dev)
         p_l = torch.empty((nq, np_), dtype=torch.int64, device=dev)
+        if args.coarse_shard == "lists":
+            gc_s = torch.empty((world, nq, np_), dtype=torch.float32, device=dev)
+            gc_l = torch.empty((world, nq, np_), dtype=torch.int64, device=dev)
+            p_s = torch.empty((nq, np_), dtype=torch.float32, device=dev)
 
     def sharded_search(q_ptr, ln, st):
-        """list-sharded batch: local coarse -> all-gather -> merged probes -> local list scan -> all-gather -> merged top-k"""
-        ix.coarse_device(nq, q_ptr, np_, rank * nlist_local, (rank + 1) * nlist_local, c_s.data_ptr(), c_l.data_ptr(), stream=st.cuda_stream)
-        with torch.cuda.stream(st):
-            dist.all_gather_into_tensor(gc_s.view(-1), c_s.view(-1))
-            dist.all_gather_into_tensor(gc_l.view(-1), c_l.view(-1))
-        b200vs.merge_topk_device(local_rank, world, nq, np_, gc_s.data_ptr(), gc_l.data_ptr(), p_s.data_ptr(), p_l.data_ptr(), st.cuda_stream)
+        """list-sharded batch: coarse (sharded) -> all-gather -> local list scan -> all-gather -> merged top-k"""
+        if args.coarse_shard == "queries":
+            ix.coarse_device(bq, q_ptr + rank * bq * d * 4, np_, 0, nlist, c_s.data_ptr(), c_l.data_ptr(), stream=st.cuda_stream)
+            launches[0] += ix.stats()[0]
+            with torch.cuda.stream(st):
+                dist.all_gather_into_tensor(p_l.view(-1), c_l[:bq].view(-1))
+        else:
+            ix.coarse_device(nq, q_ptr, np_, rank * nlist_local, (rank + 1) * nlist_local, c_s.data_ptr(), c_l.data_ptr(), stream=st.cuda_stream)
+            launches[0] += ix.stats()[0]
+            with torch.cuda.stream(st):
+                dist.all_gather_into_tensor(gc_s.view(-1), c_s.view(-1))
+                dist.all_gather_into_tensor(gc_l.view(-1), c_l.view(-1))
+            b200vs.merge_topk_device(local_rank, world, nq, np_, gc_s.data_ptr(), gc_l.data_ptr(), p_s.data_ptr(), p_l.data_ptr(), st.cuda_stream)
+            launches[0] += 1
         ix.search_probes_device(nq, q_ptr, k, p_l.data_ptr(), np_, out_d[ln].data_ptr(), out_i[ln].data_ptr(), stream=st.cuda_stream, sp=sp)
-        launches[0] += ix.stats()[0] + 6
+        launches[0] += ix.stats()[0]
         with torch.cuda.stream(st):
             dist.all_gather_into_tensor(g_d[ln].view(-1), out_d[ln].view(-1))
             dist.all_gather_into_tensor(g_i[ln].view(-1), out_i[ln].view(-1))
@@ -395,16 +410,30 @@ def main():
     # ---- roofline of the dominant kernel (separate, profiled pass; never part of the timed numbers) ----
     ix.set_profiling(True)
     kt, rows = [], 0
+    phase_ms = {}
     for i in range(3):
         if world > 1:
             sharded_search(q_dev[i % nbatches].data_ptr(), 0, stream)
+            torch.cuda.synchronize()
+            phase_ms = ix.phase_times()  # of the probe-driven list scan; the coarse call is timed below
         else:
             ix.search_device(nq, q_dev[i % nbatches].data_ptr(), k, out_d[0].data_ptr(), out_i[0].data_ptr(), stream=stream.cuda_stream, sp=sp)
         torch.cuda.synchronize()
         st = ix.stats()
         kt.append(st[3] / 1e9)
         rows = st[4]
+        if world == 1:
+            phase_ms = ix.phase_times()
     prof_stats = list(st)
+    if world > 1:  # coarse call alone
+        if args.coarse_shard == "queries":
+            ix.coarse_device(bq, q_dev[0].data_ptr() + rank * bq * d * 4, np_, 0, nlist, c_s.data_ptr(), c_l.data_ptr(), stream=stream.cuda_stream)
+        else:
+            ix.coarse_device(nq, q_dev[0].data_ptr(), np_, rank * nlist_local, (rank + 1) * nlist_local, c_s.data_ptr(), c_l.data_ptr(), stream=stream.cuda_stream)
+        torch.cuda.synchronize()
+        cp = ix.phase_times()
+        for kk in ("coarse_prep", "coarse_scan", "coarse_final"):
+            phase_ms[kk] = cp[kk]
     ix.set_profiling(False)
     peak, how = measured_peaks()
     kern_s = float(np.mean(kt)) if kt and min(kt) > 0 else None
@@ -451,7 +480,7 @@ def main():
                 "single_stream": {"value": nq * args.steps / (ms_single / 1e3), "unit": "queries/s", "ms_per_step": ms_single / args.steps,
                                   "note": "same K steps strictly back to back on one stream"},
                 "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "recall_at_10_vs_oracle": recall_vs_oracle, "build_seconds": build_s, "search_stats": ix.stats(), "profile_stats": prof_stats}
+                "recall_at_10_vs_oracle": recall_vs_oracle, "build_seconds": build_s, "search_stats": ix.stats(), "profile_stats": prof_stats, "phase_ms": {a: round(v, 4) for a, v in phase_ms.items()}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

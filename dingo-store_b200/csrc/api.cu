@@ -161,9 +161,10 @@ int b200vs_search_device(b200vs_index* h, int64_t nq, const float* xq_dev, int32
     ix->set_device();
     LaneGuard lane(ix, (cudaStream_t)stream);
     cudaStream_t s = lane.stream;
-    for (int i = 0; i < 8; ++i) ix->stats[i] = 0;
+    ix->reset_stats();
     SearchCtx sc = make_ctx(ix, sp, s);
     ix->search_dev(nq, xq_dev, k, sc, out_dist_dev, (long long*)out_ids_dev, s);
+    ix->phases_finish(s);
     if (!stream) B200VS_CUDA(cudaStreamSynchronize(s));  // NULL stream: library-owned stream, results ready on return
     return B200VS_OK;
   });
@@ -177,7 +178,9 @@ int b200vs_coarse_device(b200vs_index* h, int64_t nq, const float* xq_dev, int32
     std::shared_lock<std::shared_mutex> rl(ix->rw);
     ix->set_device();
     LaneGuard lane(ix, (cudaStream_t)stream);
+    ix->reset_stats();
     ix->coarse_range_dev(nq, xq_dev, nprobe, list_begin, list_end, out_score_dev, (long long*)out_lists_dev, lane.stream);
+    ix->phases_finish(lane.stream);
     if (!stream) B200VS_CUDA(cudaStreamSynchronize(lane.stream));
     return B200VS_OK;
   });
@@ -193,9 +196,10 @@ int b200vs_search_probes_device(b200vs_index* h, int64_t nq, const float* xq_dev
     std::shared_lock<std::shared_mutex> rl(ix->rw);
     ix->set_device();
     LaneGuard lane(ix, (cudaStream_t)stream);
-    for (int i = 0; i < 8; ++i) ix->stats[i] = 0;
+    ix->reset_stats();
     SearchCtx sc = make_ctx(ix, sp, lane.stream);
     ix->search_probes_dev(nq, xq_dev, k, (const long long*)probes_dev, nprobe, sc, out_dist_dev, (long long*)out_ids_dev, lane.stream);
+    ix->phases_finish(lane.stream);
     if (!stream) B200VS_CUDA(cudaStreamSynchronize(lane.stream));
     return B200VS_OK;
   });
@@ -212,13 +216,14 @@ int b200vs_search(b200vs_index* h, int64_t nq, const float* xq, int32_t k, const
     ix->set_device();
     LaneGuard lane(ix, nullptr);  // host-pointer call: a free lane on its own stream, so concurrent callers overlap
     cudaStream_t s = lane.stream;
-    for (int i = 0; i < 8; ++i) ix->stats[i] = 0;
+    ix->reset_stats();
     float* dq = ix->scratch.alloc<float>((size_t)nq * ix->dim);
     float* dd = ix->scratch.alloc<float>((size_t)nq * k);
     long long* di = ix->scratch.alloc<long long>((size_t)nq * k);
     B200VS_CUDA(cudaMemcpyAsync(dq, xq, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice, s));
     SearchCtx sc = make_ctx(ix, sp, s);
     ix->search_dev(nq, dq, k, sc, dd, di, s);
+    ix->phases_finish(s);
     B200VS_CUDA(cudaMemcpyAsync(out_dist, dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
     B200VS_CUDA(cudaMemcpyAsync(out_ids, di, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s));
     B200VS_CUDA(cudaStreamSynchronize(s));
@@ -244,6 +249,7 @@ int b200vs_range_search(b200vs_index* h, int64_t nq, const float* xq, float radi
     B200VS_CUDA(cudaMemcpyAsync(dq, xq, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice, s));
     SearchCtx sc = make_ctx(ix, sp, s);
     ix->range_search_dev(nq, dq, radius, max_results, sc, dd, di, dc, s);
+    ix->phases_finish(s);
     B200VS_CUDA(cudaMemcpyAsync(out_dist, dd, (size_t)nq * max_results * 4, cudaMemcpyDeviceToHost, s));
     B200VS_CUDA(cudaMemcpyAsync(out_ids, di, (size_t)nq * max_results * 8, cudaMemcpyDeviceToHost, s));
     B200VS_CUDA(cudaMemcpyAsync(out_counts, dc, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
@@ -285,6 +291,14 @@ int b200vs_merge_topk_device(int32_t device, int32_t nparts, int64_t nq, int32_t
     if (nparts <= 0 || nq <= 0 || k <= 0 || !parts_dist || !parts_ids || !out_dist || !out_ids) fail(B200VS_EILLEGAL_PARAMETERS, "bad merge arguments");
     B200VS_CUDA(cudaSetDevice(device));
     launch_merge_api(nparts, nq, k, parts_dist, (const long long*)parts_ids, out_dist, (long long*)out_ids, (cudaStream_t)stream);
+    return B200VS_OK;
+  });
+}
+
+int b200vs_last_phase_times(b200vs_index* h, float ms[16]) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    for (int i = 0; i < 16; ++i) ms[i] = i < IndexBase::PH_COUNT ? ix->phase_ms[i] : 0.f;
     return B200VS_OK;
   });
 }

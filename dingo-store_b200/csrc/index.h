@@ -132,6 +132,30 @@ struct IndexBase {
     void release(size_t m) { ix->cur().s.used = m; }
   } scratch{this};
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // profiling only (one caller at a time): CUDA-event marks between the phases of a search, b200vs_last_phase_times
+  enum Phase { PH_COARSE_PREP = 0, PH_COARSE_SCAN, PH_COARSE_FINAL, PH_PLAN, PH_SAMPLE, PH_TAU, PH_CAPTURE, PH_FINAL, PH_FALLBACK, PH_OTHER, PH_COUNT };
+  float phase_ms[PH_COUNT] = {0};
+  std::vector<std::pair<int, cudaEvent_t>> phase_marks;
+  void phase(int id, cudaStream_t s) {  // "phase id starts here"
+    if (!profiling) return;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    phase_marks.emplace_back(id, e);
+  }
+  void phases_finish(cudaStream_t s) {
+    if (phase_marks.empty()) return;
+    phase(-1, s);
+    cudaEventSynchronize(phase_marks.back().second);
+    for (size_t i = 0; i + 1 < phase_marks.size(); ++i) {
+      float ms = 0.f;
+      if (phase_marks[i].first >= 0 && cudaEventElapsedTime(&ms, phase_marks[i].second, phase_marks[i + 1].second) == cudaSuccess)
+        phase_ms[phase_marks[i].first] += ms;
+    }
+    for (auto& m : phase_marks) cudaEventDestroy(m.second);
+    phase_marks.clear();
+  }
+  void reset_stats() { for (auto& v : stats) v = 0; for (auto& v : phase_ms) v = 0.f; }
   bool profiling = false;  // b200vs_set_profiling: time the dominant scan kernel with CUDA events
   bool loading = false;    // Load(): rows come back exactly as stored (already normalised for cosine)
   virtual int export_nlist() const { return 1; }

@@ -64,20 +64,21 @@ static void run_scan_impl(IndexBase* ix, const ScanJob& job, int64_t nq, const f
 
   const size_t smem1 = scan_smem_bytes(job.d, job.mode == 0 ? 1 : job.nprobe, cap);
   const size_t smem2 = BlockSelect::smem_bytes(cap);
-  dim3 grid(nsplit, (unsigned)nq);
+  const unsigned slots = qcount ? (unsigned)std::min<int64_t>(nq, 64) : (unsigned)nq;  // mapped launch: CTAs stride over the live slots
+  dim3 grid(nsplit, slots);
   ScopedKernelTimer timer(ix, s, ix->profiling && job.dominant);
   if (job.l2) {
     ensure_smem(scan_select_kernel<true>, smem1);
     scan_select_kernel<true><<<grid, SCAN_THREADS, smem1, s>>>(a);
     timer.stop();
     ensure_smem(merge_select_kernel<true>, smem2);
-    merge_select_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, nsplit, k, cap, out_dist, out_raw, out_ids, out_counts, qmap, qcount);
+    merge_select_kernel<true><<<slots, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, nsplit, k, cap, out_dist, out_raw, out_ids, out_counts, qmap, qcount);
   } else {
     ensure_smem(scan_select_kernel<false>, smem1);
     scan_select_kernel<false><<<grid, SCAN_THREADS, smem1, s>>>(a);
     timer.stop();
     ensure_smem(merge_select_kernel<false>, smem2);
-    merge_select_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, nsplit, k, cap, out_dist, out_raw, out_ids, out_counts, qmap, qcount);
+    merge_select_kernel<false><<<slots, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, nsplit, k, cap, out_dist, out_raw, out_ids, out_counts, qmap, qcount);
   }
   B200VS_CUDA(cudaGetLastError());
   ix->launch_count(2);

@@ -46,15 +46,8 @@ inline size_t scan_smem_bytes(int d, int nprobe, int pool_cap) {
 }
 
 template <bool L2>
-static __global__ void __launch_bounds__(SCAN_THREADS) scan_select_kernel(const ScanArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
+static __device__ __forceinline__ void scan_select_body(const ScanArgs& a, unsigned char* smem, const int slot, const int split, const int qi) {
   const int d = a.d;
-  const int slot = blockIdx.y, split = blockIdx.x;
-  int qi = slot;
-  if (a.qcount) {
-    if (slot >= *a.qcount) return;
-    qi = a.qmap[slot];
-  }
   float* qs = reinterpret_cast<float*>(smem);
   const size_t qbytes = ((size_t)d * 4 + 15) / 16 * 16;
   int* prefix = reinterpret_cast<int*>(smem + qbytes);
@@ -134,6 +127,19 @@ static __global__ void __launch_bounds__(SCAN_THREADS) scan_select_kernel(const 
   }
 }
 
+// Plain launch: grid (nsplit, nq).  Mapped launch (a.qcount != NULL, the re-run of uncertified queries): a small grid in y
+// strides over the *a.qcount live slots, so the usual "nothing to redo" case costs a handful of empty CTAs.
+template <bool L2>
+static __global__ void __launch_bounds__(SCAN_THREADS) scan_select_kernel(const ScanArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  if (!a.qcount) { scan_select_body<L2>(a, smem, blockIdx.y, blockIdx.x, blockIdx.y); return; }
+  const int n = *a.qcount;
+  for (int slot = blockIdx.y; slot < n; slot += gridDim.y) {
+    scan_select_body<L2>(a, smem, slot, blockIdx.x, a.qmap[slot]);
+    __syncthreads();
+  }
+}
+
 // Merge the per-split partial lists of each query and emit results.
 //   out_dist: API semantics (L2: squared distance; IP: 1 - ip)        [nq, k] or NULL
 //   out_raw : raw metric value (L2 distance or ip)                     [nq, k] or NULL
@@ -146,12 +152,9 @@ static __global__ void __launch_bounds__(SCAN_THREADS) merge_select_kernel(const
                                                                     long long* out_ids, int* out_counts,
                                                                     const int* qmap, const int* qcount) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int slot = blockIdx.x;
-  int qi = slot;
-  if (qcount) {
-    if (slot >= *qcount) return;
-    qi = qmap[slot];
-  }
+  const int nslots = qcount ? *qcount : (int)gridDim.x;
+  for (int slot = blockIdx.x; slot < nslots; slot += gridDim.x) {
+  const int qi = qmap ? qmap[slot] : slot;
   BlockSelect sel;
   sel.init(smem, pool_cap, k);
   const long long tot = (long long)nparts * k;
@@ -193,6 +196,8 @@ static __global__ void __launch_bounds__(SCAN_THREADS) merge_select_kernel(const
     out_ids[(size_t)qi * k + i] = id;
   }
   if (out_counts && threadIdx.x == 0) out_counts[qi] = have;
+  __syncthreads();
+  }
 }
 
 // k-way merge of API-semantics parts [nparts, nq, k] (multi-GPU / sibling-index merge,

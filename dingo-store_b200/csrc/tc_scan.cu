@@ -665,7 +665,7 @@ __device__ int window_select(const unsigned long long* keys, int n, int k, float
 
 constexpr int FIN_THREADS = 128;   // finish kernels: many small CTAs hide their barrier / gather latency better than few big ones
 constexpr int FIN_MAXW = 1024;     // in-window rows re-scored per query on the fast path (more -> exact re-run)
-constexpr int COARSE_FAST = 4096;  // coarse rows handled by the one-sort path
+constexpr int COARSE_FAST = 8192;  // coarse rows handled by the register-select / one-sort path
 
 template <bool L2>
 static __global__ void __launch_bounds__(SCAN_THREADS)
@@ -712,10 +712,11 @@ template <bool L2>
 static __global__ void __launch_bounds__(SCAN_THREADS)
 tc_coarse_final_fast_kernel(const float* __restrict__ dense, long long ld, int nrows, const float* __restrict__ qnorm, float max_norm,
                             const float* __restrict__ q, const float* __restrict__ vecs, int d, int k, int maxw,
-                            long long id_offset, int api_scores, long long* out_probes, float* out_raw) {
+                            long long id_offset, int api_scores, long long* out_probes, float* out_raw, const int* redo) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_m;
   const int qi = blockIdx.x;
+  if (redo && !redo[qi]) return;  // only the queries the register-select kernel could not finish
   float* qs = reinterpret_cast<float*>(smem);
   const size_t qbytes = ((size_t)d * 4 + 15) / 16 * 16;
   long long* ex_id = reinterpret_cast<long long*>(smem + qbytes);                       // [maxw]   maxw = pow2(nrows)
@@ -735,6 +736,157 @@ tc_coarse_final_fast_kernel(const float* __restrict__ dense, long long ld, int n
       const float v = i < have ? ord2f(ex_kd[i]) : 0.f;
       const float raw = L2 ? v : -v;
       out_raw[(size_t)qi * k + i] = api_scores ? v : raw;  // api_scores: the ranking score itself (L2 distance | -ip), ascending
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Register-resident select (coarse finish): each of SEL_THREADS threads holds KPT keys, so a query's whole score row
+// lives in registers and the CTA needs only ~13 KB of shared memory (8 CTAs per SM hide each other's barriers).
+// ---------------------------------------------------------------------------------------------
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_BINS = 1024;   // histogram bins per narrowing step (10 bits)
+constexpr int SEL_WCAP = 512;    // window rows re-scored per query (more -> the one-sort fallback kernel)
+
+struct SelShared {
+  int hist[SEL_BINS];
+  uint32_t red[2][SEL_THREADS / 32];
+  uint32_t lo, hi;
+  int k, c_le, m, ns;
+};
+
+// k-th smallest (k >= 1, at least k live keys) of the CTA's keys; 0xFFFFFFFF marks an empty slot.  Range-normalised
+// radix select: bin = (key - lo) >> shift over the live range [lo, hi], narrow to the bin that holds the k-th key and
+// repeat until bins are one key wide (two steps for the ~2^20-wide ranges of real score rows; never more than four).
+// On return S.c_le = number of keys <= the result when known exactly, else k + 1.
+template <int KPT>
+__device__ uint32_t reg_kth_key(const uint32_t (&key)[KPT], int k, SelShared& S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+#pragma unroll
+  for (int j = 0; j < KPT; ++j)
+    if (key[j] != 0xFFFFFFFFu) { mn = min(mn, key[j]); mx = max(mx, key[j]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+  if (lane == 0) { S.red[0][warp] = mn; S.red[1][warp] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t a = 0xFFFFFFFFu, b = 0u;
+    for (int w = 0; w < SEL_THREADS / 32; ++w) { a = min(a, S.red[0][w]); b = max(b, S.red[1][w]); }
+    S.lo = a; S.hi = b; S.k = k; S.c_le = k + 1;
+  }
+  __syncthreads();
+  for (;;) {
+    const uint32_t lo = S.lo, hi = S.hi;
+    const int kk = S.k;
+    const uint32_t range = hi - lo;
+    if (range == 0) return lo;  // every remaining key is equal
+    const int bits = 32 - __clz(range);
+    const int shift = max(0, bits - 10);
+    for (int i = threadIdx.x; i < SEL_BINS; i += SEL_THREADS) S.hist[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < KPT; ++j)
+      if (key[j] >= lo && key[j] <= hi) atomicAdd(&S.hist[(key[j] - lo) >> shift], 1);
+    __syncthreads();
+    if (warp == 0) {  // locate the bin that holds the kk-th key: 32 bins per lane
+      int sum = 0;
+      for (int j = 0; j < SEL_BINS / 32; ++j) sum += S.hist[lane * (SEL_BINS / 32) + j];
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      const int before = incl - sum;
+      if (before < kk && kk <= incl) {  // exactly one lane
+        int acc = before;
+        for (int j = 0; j < SEL_BINS / 32; ++j) {
+          const int c = S.hist[lane * (SEL_BINS / 32) + j];
+          if (acc < kk && kk <= acc + c) {
+            const uint32_t nlo = lo + ((uint32_t)(lane * (SEL_BINS / 32) + j) << shift);
+            S.lo = nlo;
+            S.hi = min(hi, nlo + ((1u << shift) - 1u));
+            S.k = kk - acc;
+            if (shift == 0) S.c_le = (k - kk) + acc + c;
+            break;
+          }
+          acc += c;
+        }
+      }
+    }
+    __syncthreads();
+    if (shift == 0) return S.lo;
+  }
+}
+
+// Coarse finish: top-nprobe rows of one query's dense score row.
+//   full mode (out_raw != NULL or ties at the k-th score): re-score every row within 2*eps of the k-th approximate score
+//     exactly and emit them in exact (score, row) order.
+//   set mode  (probe tables, whose order nobody reads): rows more than 2*eps below the k-th score are certainly among
+//     the exact top-k (only the k - 1 rows below it can beat them), rows more than 2*eps above are certainly not; only the
+//     few rows in between are re-scored to fill the remaining slots.
+// flags[qi] = 1 when the window overflowed SEL_WCAP: the one-sort kernel then redoes that query.
+template <bool L2, int KPT>
+static __global__ void __launch_bounds__(SEL_THREADS)
+tc_coarse_select_kernel(const float* __restrict__ dense, long long ld, int nrows, const float* __restrict__ qnorm, float max_norm,
+                        const float* __restrict__ q, const float* __restrict__ vecs, int d, int k, long long id_offset, int api_scores,
+                        long long* out_probes, float* out_raw, int* flags) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ SelShared S;
+  __shared__ int s_rows[SEL_WCAP];
+  __shared__ uint32_t s_kd[SEL_WCAP];
+  __shared__ long long s_id[SEL_WCAP];
+  const int qi = blockIdx.x;
+  float* qs = reinterpret_cast<float*>(smem);
+  for (int i = threadIdx.x; i < d; i += SEL_THREADS) qs[i] = q[(size_t)qi * d + i];
+  uint32_t key[KPT];
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) {
+    const int r = threadIdx.x + j * SEL_THREADS;
+    key[j] = r < nrows ? f2ord(dense[(size_t)qi * ld + r]) : 0xFFFFFFFFu;
+  }
+  const uint32_t kth = reg_kth_key<KPT>(key, k, S);  // barriers inside: qs is visible afterwards
+  const float a_k = ord2f(kth);
+  const float two_eps = 2.f * tc_eps(L2, qnorm[qi], max_norm, d, true);
+  const uint32_t thr_hi = f2ord(__fadd_ru(a_k, two_eps));
+  const bool set_mode = out_raw == nullptr && S.c_le == k;
+  const uint32_t thr_lo = f2ord(__fsub_rd(a_k, two_eps));
+  if (threadIdx.x == 0) { S.m = 0; S.ns = 0; }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) {
+    if (key[j] > thr_hi) continue;  // empty slots (0xFFFFFFFF) drop out here too
+    const int r = threadIdx.x + j * SEL_THREADS;
+    if (set_mode && key[j] <= thr_lo) out_probes[(size_t)qi * k + atomicAdd(&S.ns, 1)] = r + id_offset;
+    else { const int pos = atomicAdd(&S.m, 1); if (pos < SEL_WCAP) s_rows[pos] = r; }
+  }
+  __syncthreads();
+  const int m = S.m, ns = S.ns;
+  if (m > SEL_WCAP) {  // degenerate score row (many near-equal scores): redo on the one-sort path
+    if (threadIdx.x == 0) flags[qi] = 1;
+    return;
+  }
+  if (threadIdx.x == 0) flags[qi] = 0;
+  const int quad = threadIdx.x >> 2, t = threadIdx.x & 3;
+  const bool vec = (d & 3) == 0;
+  for (int base = 0; base < m; base += SEL_THREADS / 4) {
+    const int i = base + quad;
+    const bool valid = i < m;
+    const long long row = (long long)s_rows[valid ? i : 0];
+    const float v = quad_distance<L2>(vecs + (size_t)row * d, qs, d, t, vec);
+    if (valid && t == 0) { s_kd[i] = f2ord(L2 ? v : -v); s_id[i] = row; }
+  }
+  int e2 = 2;
+  while (e2 < m) e2 <<= 1;
+  __syncthreads();
+  for (int i = m + threadIdx.x; i < e2; i += SEL_THREADS) { s_kd[i] = KEY_SENTINEL_D; s_id[i] = KEY_SENTINEL_ID; }
+  __syncthreads();
+  block_sort_pair(s_kd, s_id, e2);
+  const int need = k - ns;  // slots still open (set mode), all k otherwise
+  for (int i = threadIdx.x; i < need; i += SEL_THREADS) {
+    const bool have = i < m;
+    out_probes[(size_t)qi * k + ns + i] = have ? s_id[i] + id_offset : -1;
+    if (out_raw) {
+      const float v = have ? ord2f(s_kd[i]) : 0.f;
+      out_raw[(size_t)qi * k + i] = api_scores ? v : (L2 ? v : -v);
     }
   }
 }
@@ -1078,6 +1230,7 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   const int d = ix->dim;
   const int cap = tc_cand_cap(k);
   auto& S = ix->scratch;
+  ix->phase(IndexBase::PH_PLAN, s);
   TcPlan P = tc_prepare(ix, v, nq, q, probes, nprobe, s);
   float* sample = S.alloc<float>((size_t)P.sbound * TC_NQT * TC_SAMPLE);
   float* tau = S.alloc<float>(nq);
@@ -1097,16 +1250,20 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
 
   // 1) sample pass -> per-query capture thresholds
   p.mode = 0; p.work_counter = P.work;
+  ix->phase(IndexBase::PH_SAMPLE, s);
   tc_launch(P, p, P.sbound, s);
+  ix->phase(IndexBase::PH_TAU, s);
   tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, (size_t)TAU_PL * 8 + std::max(sel_smem, (size_t)TAU_SORT * 8), s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, k, pool, tau);
   // 2) capture pass: stream every probed list chunk once, keep rows under the threshold
   p.mode = 1; p.work_counter = P.work + 1;
+  ix->phase(IndexBase::PH_CAPTURE, s);
   {
     ScopedKernelTimer timer(ix, s, ix->profiling);
     tc_launch(P, p, P.bound, s);
     timer.stop();
   }
   // 3) window select + exact rerank + certification
+  ix->phase(IndexBase::PH_FINAL, s);
   const size_t fast_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_MAXW * 16 + (size_t)cap * 8;
   if (fast_smem <= 200 * 1024) {  // one 64-bit sort of the captured rows + a small exact sort
     if (l2) tc_final_fast_kernel<true><<<(unsigned)nq, SCAN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
@@ -1125,7 +1282,9 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   job.l2 = l2; job.vecs = v.vecs; job.ids = v.ids; job.d = d; job.sc = &sc;
   if (!v.flat) { job.mode = 1; job.probes = probes; job.nprobe = nprobe; job.list_off = v.list_off; job.list_len = v.list_len; }
   else { job.mode = 0; job.n = v.arena_rows; }
+  ix->phase(IndexBase::PH_FALLBACK, s);
   run_scan_mapped(ix, job, nq, qmap, qcount, q, k, out_dist, out_ids, s);
+  ix->phase(IndexBase::PH_OTHER, s);
   if (ix->profiling) {
     int h = 0;
     B200VS_CUDA(cudaMemcpyAsync(&h, qcount, 4, cudaMemcpyDeviceToHost, s));
@@ -1164,6 +1323,7 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   int* totals = S.alloc<int>(4);
   int* work = S.alloc<int>(4);
   float* dense = S.alloc<float>((size_t)nq * nrows);
+  ix->phase(IndexBase::PH_COARSE_PREP, s);
   B200VS_CUDA(cudaMemsetAsync(work, 0, 16, s));
   tc_prep_queries_split_kernel<<<(unsigned)cdiv(nq * 32, 256), 256, 0, s>>>(q, nq, d, qhi, qlo, qnorm);
   tc_coarse_items_kernel<<<(unsigned)cdiv(nitems, 128), 128, 0, s>>>(nrows, (int)nq, chunk, items, totals);
@@ -1177,13 +1337,26 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   const CUtensorMap l16 = make_tmap(qlo, nq, d, 16), l32 = make_tmap(qlo, nq, d, 32), l64 = make_tmap(qlo, nq, d, 64), l128 = make_tmap(qlo, nq, d, 128);
   const int grid = (int)std::min<int64_t>(g_num_sms, std::max(1, nitems));
   p.work_counter = work; p.split = 1; p.dense_accum = 0; p.add_norm = 1;
+  ix->phase(IndexBase::PH_COARSE_SCAN, s);
   tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(a_hi, a_hi, b16, b32, b64, b128, a_lo, l16, l32, l64, l128, b16, p);
   B200VS_CUDA(cudaGetLastError());
+  ix->phase(IndexBase::PH_COARSE_FINAL, s);
   if (nrows <= COARSE_FAST && nprobe <= nrows) {
+    // register-resident select (8 CTAs per SM), then the one-sort kernel for the queries it flagged (normally none)
+    int* redo = S.alloc<int>(nq);
+    const size_t qsm = ((size_t)d * 4 + 15) / 16 * 16;
+    const int kpt = (nrows + SEL_THREADS - 1) / SEL_THREADS;
+#define B200VS_SEL(L2_, KPT_) tc_coarse_select_kernel<L2_, KPT_><<<(unsigned)nq, SEL_THREADS, qsm, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw, redo)
+    if (kpt <= 4) { if (l2) B200VS_SEL(true, 4); else B200VS_SEL(false, 4); }
+    else if (kpt <= 8) { if (l2) B200VS_SEL(true, 8); else B200VS_SEL(false, 8); }
+    else if (kpt <= 16) { if (l2) B200VS_SEL(true, 16); else B200VS_SEL(false, 16); }
+    else { if (l2) B200VS_SEL(true, 32); else B200VS_SEL(false, 32); }
+#undef B200VS_SEL
     const int maxw = std::max(2, next_pow2(nrows));
     const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)maxw * 24;
-    if (l2) tc_coarse_final_fast_kernel<true><<<(unsigned)nq, FIN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw);
-    else tc_coarse_final_fast_kernel<false><<<(unsigned)nq, FIN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw);
+    if (l2) tc_coarse_final_fast_kernel<true><<<(unsigned)nq, FIN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw, redo);
+    else tc_coarse_final_fast_kernel<false><<<(unsigned)nq, FIN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw, redo);
+    ix->launch_count(1);
   } else {
     const int pool = select_pool_cap(nprobe, SCAN_THREADS);
     const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + BlockSelect::smem_bytes(pool);
@@ -1191,6 +1364,7 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
     else tc_coarse_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw);
   }
   B200VS_CUDA(cudaGetLastError());
+  ix->phase(IndexBase::PH_OTHER, s);
   ix->launch_count(4);
 }
 

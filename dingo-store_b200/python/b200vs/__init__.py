@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "b200vs_create", "b200vs_destroy", "b200vs_train", "b200vs_set_trained_state", "b200vs_get_trained_state",
     "b200vs_add_with_ids", "b200vs_remove_ids", "b200vs_search", "b200vs_search_device", "b200vs_coarse_device", "b200vs_search_probes_device", "b200vs_range_search",
     "b200vs_count", "b200vs_deleted_count", "b200vs_memory_size", "b200vs_is_trained", "b200vs_dimension",
-    "b200vs_save", "b200vs_load", "b200vs_export_lists", "b200vs_merge_topk_device", "b200vs_last_search_stats", "b200vs_set_profiling",
+    "b200vs_save", "b200vs_load", "b200vs_export_lists", "b200vs_merge_topk_device", "b200vs_last_search_stats", "b200vs_last_phase_times", "b200vs_set_profiling",
     "b200vs_last_error", "b200vs_version",
 ]
 
@@ -84,6 +84,7 @@ def lib():
     L.b200vs_export_lists.argtypes = [vp, vp, vp, vp, vp]
     L.b200vs_merge_topk_device.argtypes = [i32, i32, i64, i32, vp, vp, vp, vp, vp]
     L.b200vs_last_search_stats.argtypes = [vp, ctypes.POINTER(i64 * 8)]
+    L.b200vs_last_phase_times.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 16)]
     L.b200vs_set_profiling.argtypes = [vp, ctypes.c_int]
     L.b200vs_last_error.restype = ctypes.c_char_p
     L.b200vs_version.restype = ctypes.c_char_p
@@ -236,6 +237,14 @@ class Index:
         a = (ctypes.c_int64 * 8)()
         _check(self.L.b200vs_last_search_stats(self.h, ctypes.byref(a)))
         return list(a)
+
+    PHASES = ("coarse_prep", "coarse_scan", "coarse_final", "plan", "sample", "tau", "capture", "final", "fallback", "other")
+
+    def phase_times(self):
+        """{phase: device ms} of the last search (profiling mode only)."""
+        a = (ctypes.c_float * 16)()
+        _check(self.L.b200vs_last_phase_times(self.h, ctypes.byref(a)))
+        return {n: float(a[i]) for i, n in enumerate(self.PHASES)}
 
     def set_profiling(self, on):
         _check(self.L.b200vs_set_profiling(self.h, int(bool(on))))

@@ -152,6 +152,11 @@ int b200vs_search_probes_device(b200vs_index* idx, int64_t nq, const float* xq_d
  * [7] its tensor-core work (128-row tiles x padded query columns).  Profiling synchronises the stream
  * inside the call: never leave it on in a timed run. */
 int b200vs_last_search_stats(b200vs_index* idx, int64_t stats[8]);
+/* With profiling on: device milliseconds (CUDA events on the launch stream) the last search spent in each phase of the
+ * IVF tile path: [0] coarse prep, [1] coarse scan, [2] coarse select + exact re-score, [3] work planning + query
+ * gather, [4] sample pass, [5] thresholds, [6] list scan (capture), [7] final select + exact re-score, [8] exact
+ * fallback for uncertified queries, [9] other.  Unused slots are 0. */
+int b200vs_last_phase_times(b200vs_index* idx, float ms[16]);
 int b200vs_set_profiling(b200vs_index* idx, int on);
 
 const char* b200vs_last_error(void);

@@ -88,6 +88,37 @@ def test_sharded_coarse_tile_path_large():
         assert np.array_equal(od.view(np.uint32), wd.view(np.uint32))
 
 
+def test_coarse_split_by_queries_equals_plain_search():
+    """The other split: each 'rank' ranks a slice of the batch against ALL centroids; concatenating the probe tables
+    (what one all-gather does) and scanning them reproduces the plain search."""
+    require_gpu()
+    import torch
+    n, d, nlist, k, nprobe, nq, parts = 60000, 768, 1024, 10, 32, 1024, 4
+    ix, xb, ids = _build(b200vs.L2, n, d, nlist, 5)
+    xq = np.random.default_rng(12).random((nq, d), dtype=np.float32)
+    wd, wi = ix.search(xq, k, nprobe=nprobe)
+    sp, _keep = b200vs.make_search_params(nprobe=nprobe)
+    q = torch.from_numpy(xq).cuda()
+    torch.cuda.synchronize()
+    ts = torch.cuda.Stream()
+    bq = nq // parts
+    sc = torch.empty((nq, nprobe), dtype=torch.float32, device="cuda")
+    pl = torch.empty((nq, nprobe), dtype=torch.int64, device="cuda")
+    for r in range(parts):
+        ix.coarse_device(bq, q[r * bq:].data_ptr(), nprobe, 0, nlist, sc[r * bq:].data_ptr(), pl[r * bq:].data_ptr(), stream=ts.cuda_stream)
+    od = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    oi = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    ix.search_probes_device(nq, q.data_ptr(), k, pl.data_ptr(), nprobe, od.data_ptr(), oi.data_ptr(), stream=ts.cuda_stream, sp=sp)
+    torch.cuda.synchronize()
+    assert np.array_equal(oi.cpu().numpy(), wi)
+    assert np.array_equal(od.cpu().numpy().view(np.uint32), wd.view(np.uint32))
+    o = oracle_lib.load()
+    cent = ix.get_trained_state()[32:].view(np.float32).reshape(nlist, d)
+    cd, ci = o.flat_search(oracle_lib.L2, cent, np.arange(nlist, dtype=np.int64), xq[:64], nprobe)
+    assert np.array_equal(pl.cpu().numpy()[:64], ci)
+    assert np.array_equal(sc.cpu().numpy()[:64].view(np.uint32), cd.view(np.uint32))
+
+
 def test_coarse_device_rejects_bad_range():
     require_gpu()
     import torch
