@@ -438,8 +438,17 @@ def main():
     peak, how = measured_peaks()
     kern_s = float(np.mean(kt)) if kt and min(kt) > 0 else None
     alg_bytes = rows * (d * 4 + 8)
+    # DRAM traffic of the same kernel from the committed ncu --set full capture (only for the workload it was taken on)
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "round1", "ncu_traffic.json")
+    if world == 1 and (args.nb, args.dim, args.nlist, args.nprobe, args.batch, args.k) == (1_000_000, 768, 1024, 32, 1024, 10) and os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            traffic, traffic_src = int(tj["dram_bytes_per_launch"]), tj["source"]
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "achieved": (alg_bytes / kern_s / 1e9) if kern_s else None, "peak": peak, "unit": "GB/s",
-                "frac": (alg_bytes / kern_s / 1e9 / peak) if kern_s else None, "traffic": None,
+                "frac": (alg_bytes / kern_s / 1e9 / peak) if kern_s else None, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "ivf list scan", "kernel_ms": kern_s * 1e3 if kern_s else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs)" if how == "measured" else "fallback 6650 GB/s"}
 
