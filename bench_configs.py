@@ -206,6 +206,55 @@ def cfg4(o, cores, n):
             "build_seconds_engine": t_build, "build_seconds_oracle": t_oracle_build, "search_stats": st}
 
 
+def cfg_calc(o, cores):
+    """the UtilService distance matrix (VectorCalcDistance), 1024 x 1024 x 768, host pointers in and out."""
+    nl = nr = 1024
+    d = 768
+    left, right = rnd(nl, d, 11), rnd(nr, d, 12)
+    out = {}
+    for name, metric in (("l2", b200vs.L2), ("cosine", b200vs.COSINE)):
+        b200vs.calc_distance(b200vs.ALGORITHM_FAISS, metric, left, right)  # warm-up (context, allocations)
+        t = time.time()
+        reps = 5
+        for _ in range(reps):
+            got = b200vs.calc_distance(b200vs.ALGORITHM_FAISS, metric, left, right)
+        gpu_s = (time.time() - t) / reps
+        ns = 64  # bounded CPU sample: 64 left rows against all right rows
+        t = time.time()
+        want, _, _ = o.calc_distance(1, oracle_lib.L2 if metric == b200vs.L2 else oracle_lib.COSINE, left[:ns], right)
+        cpu_s = (time.time() - t) * nl / ns
+        out[name] = {"pairs_per_s_e2e": nl * nr / gpu_s, "ms_e2e": gpu_s * 1e3, "bit_exact_vs_oracle": bool(np.array_equal(got[:ns].view(np.uint32), want.view(np.uint32))),
+                     "cpu_pairs_per_s_1thread": nl * nr / cpu_s}
+    return {"config": "calc_distance", "workload": f"VectorCalcDistance {nl} x {nr} x {d} f32, ALGORITHM_FAISS, host buffers (H2D + D2H inside)", **out}
+
+
+def cfg_brute(o, cores):
+    """BruteForceSearch over 200K x 768 rows streamed in 2048-row tiles (FLAGS_vector_index_bruteforce_batch_count)."""
+    n, d, nq, k, tile = 200_000, 768, 256, 10, 2048
+    xb, xq = rnd(n, d, 21), rnd(nq, d, 22)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+
+    def run(t):
+        sc = b200vs.BruteForceScan(b200vs.L2, d, xq, k)
+        for a in range(0, n, t):
+            sc.push(xb[a:a + t], ids[a:a + t])
+        return sc.finish()
+
+    run(tile)
+    res = {}
+    for t in (tile, 32768):
+        t0 = time.time()
+        gd, gi = run(t)
+        res[f"tile_{t}"] = {"seconds": time.time() - t0, "rows_per_s": n / (time.time() - t0), "queries_x_rows_per_s": nq * n / (time.time() - t0)}
+    ns = 16
+    t0 = time.time()
+    wd, wi = o.flat_search(oracle_lib.L2, xb, ids, xq[:ns], k, nthreads=cores)
+    cpu_s = (time.time() - t0) * nq / ns
+    return {"config": "bruteforce_scan", "workload": f"BruteForceSearch L2 {n} x {d} streamed from host, batch {nq}, top-{k}", **res,
+            "ids_bit_exact_vs_oracle": bool(np.array_equal(gi[:ns], wi)), "dist_bit_exact_vs_oracle": bool(np.array_equal(gd[:ns].view(np.uint32), wd.view(np.uint32))),
+            "cpu_baseline_seconds_scaled": cpu_s, "cpu_cores": cores}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,2,3,4")
@@ -215,7 +264,8 @@ def main():
     a = ap.parse_args()
     o = oracle_lib.load()
     cores = os.cpu_count() or 1
-    fns = {"1": lambda: cfg1(o, cores), "2": lambda: cfg2(o, cores), "3": lambda: cfg3(o, cores, a.pq_n), "4": lambda: cfg4(o, cores, a.hnsw_n)}
+    fns = {"1": lambda: cfg1(o, cores), "2": lambda: cfg2(o, cores), "3": lambda: cfg3(o, cores, a.pq_n), "4": lambda: cfg4(o, cores, a.hnsw_n),
+           "calc": lambda: cfg_calc(o, cores), "brute": lambda: cfg_brute(o, cores)}
     for c in a.configs.split(","):
         t0 = time.time()
         try:

@@ -3,7 +3,9 @@
 // (reference convention: butil::Status codes, never exceptions across the plugin virtual;
 // src/vector/vector_index_flat.cc:313-315, src/handler/raft_apply_handler.cc:1311-1325).
 #include <cstdio>
+#include <memory>
 #include <new>
+#include <vector>
 
 #include "index.h"
 
@@ -294,6 +296,151 @@ int b200vs_merge_topk_device(int32_t device, int32_t nparts, int64_t nq, int32_t
     return B200VS_OK;
   });
 }
+
+// ---- VectorCalcDistance: pairwise distance matrix (src/vector/vector_index_utils.cc:48-124, :193-419) ----
+int b200vs_calc_distance(int32_t device, int32_t algorithm, b200vs_metric metric, int32_t dim, int64_t nl, const float* left,
+                         int64_t nr, const float* right, float* out, float* left_out, float* right_out) {
+  return guarded([&]() -> int {
+    if (algorithm != B200VS_ALGORITHM_FAISS && algorithm != B200VS_ALGORITHM_HNSWLIB)
+      fail(B200VS_EILLEGAL_PARAMETERS, "invalid algorithm type : ALGORITHM_NONE");      // utils.cc:70-76
+    if (metric != B200VS_L2 && metric != B200VS_IP && metric != B200VS_COSINE)
+      fail(B200VS_EILLEGAL_PARAMETERS, "invalid metric_type type : METRIC_TYPE_NONE");   // utils.cc:151-157
+    if (dim <= 0 || nl < 0 || nr < 0) fail(B200VS_EILLEGAL_PARAMETERS, "bad distance-matrix shape");
+    if (nl == 0 || nr == 0) return B200VS_OK;  // CalcDistanceCore over empty operands: empty result
+    if (!left || !right || !out) fail(B200VS_EILLEGAL_PARAMETERS, "null operand");
+    B200VS_CUDA(cudaSetDevice(device));
+    cudaStream_t s = nullptr;
+    B200VS_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    DevBuf<float> dl, dr, dn, dout;
+    try {
+      dl.reserve((size_t)nl * dim, 0, s); dr.reserve((size_t)nr * dim, 0, s); dout.reserve((size_t)nl * nr, 0, s);
+      B200VS_CUDA(cudaMemcpyAsync(dl.p, left, (size_t)nl * dim * 4, cudaMemcpyHostToDevice, s));
+      B200VS_CUDA(cudaMemcpyAsync(dr.p, right, (size_t)nr * dim * 4, cudaMemcpyHostToDevice, s));
+      if (metric == B200VS_COSINE) {
+        if (algorithm == B200VS_ALGORITHM_FAISS) {  // NormalizeVectorForFaiss on copies, utils.cc:283-284
+          launch_normalize_faiss(dl.p, nl, dim, s);
+          launch_normalize_faiss(dr.p, nr, dim, s);
+        } else {                                    // NormalizeVectorForHnsw, utils.cc:407-413 (out of place)
+          dn.reserve((size_t)std::max(nl, nr) * dim, 0, s);
+          launch_normalize_hnsw(dl.p, dn.p, nl, dim, s);
+          B200VS_CUDA(cudaMemcpyAsync(dl.p, dn.p, (size_t)nl * dim * 4, cudaMemcpyDeviceToDevice, s));
+          launch_normalize_hnsw(dr.p, dn.p, nr, dim, s);
+          B200VS_CUDA(cudaMemcpyAsync(dr.p, dn.p, (size_t)nr * dim * 4, cudaMemcpyDeviceToDevice, s));
+        }
+      }
+      launch_pair_distance(metric == B200VS_L2, dl.p, nl, dr.p, nr, dim, dout.p, s);
+      B200VS_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)nl * nr * 4, cudaMemcpyDeviceToHost, s));
+      if (left_out) B200VS_CUDA(cudaMemcpyAsync(left_out, dl.p, (size_t)nl * dim * 4, cudaMemcpyDeviceToHost, s));
+      if (right_out) B200VS_CUDA(cudaMemcpyAsync(right_out, dr.p, (size_t)nr * dim * 4, cudaMemcpyDeviceToHost, s));
+      B200VS_CUDA(cudaStreamSynchronize(s));
+    } catch (...) {
+      cudaStreamSynchronize(s); dl.free(); dr.free(); dn.free(); dout.free(); cudaStreamDestroy(s);
+      throw;
+    }
+    dl.free(); dr.free(); dn.free(); dout.free();
+    cudaStreamDestroy(s);
+    return B200VS_OK;
+  });
+}
+
+// ---- streaming brute-force scan: VectorReader::BruteForceSearch (src/vector/vector_reader.cc:1873-2048) ----
+struct b200vs_scan {
+  IndexBase* flat = nullptr;  // one tile at a time
+  int64_t nq = 0;
+  int k = 0;
+  bool has_sp = false;
+  b200vs_search_params sp{};
+  std::vector<int64_t> allow;  // private copy of sp.sorted_ids (the caller's array need not outlive scan_begin)
+  cudaStream_t s = nullptr;
+  DevBuf<float> q, parts_d, out_d;      // parts = [2, nq, k]: running result, tile result
+  DevBuf<long long> parts_i, out_i;
+  int64_t pushed = 0;
+  ~b200vs_scan() {
+    if (flat) { cudaSetDevice(flat->device); }
+    if (s) cudaStreamSynchronize(s);
+    q.free(); parts_d.free(); out_d.free(); parts_i.free(); out_i.free();
+    delete flat;
+    if (s) cudaStreamDestroy(s);
+  }
+};
+
+int b200vs_scan_begin(int32_t device, b200vs_metric metric, int32_t dim, int64_t nq, const float* xq, int32_t k,
+                      const b200vs_search_params* sp, b200vs_scan** out) {
+  return guarded([&]() -> int {
+    if (!out) fail(B200VS_EILLEGAL_PARAMETERS, "out is null");
+    *out = nullptr;
+    if (dim <= 0) fail(B200VS_EVECTOR_INVALID, "vector index dimension is invalid");  // vector_reader.cc:1889-1894
+    if (metric != B200VS_L2 && metric != B200VS_IP && metric != B200VS_COSINE) fail(B200VS_EILLEGAL_PARAMETERS, "unsupported metric type");
+    if (nq <= 0 || !xq) fail(B200VS_EILLEGAL_PARAMETERS, "vector_with_ids is empty");
+    if (k <= 0) fail(B200VS_EILLEGAL_PARAMETERS, "topk must be > 0");
+    b200vs_params p{};
+    p.device = device;
+    std::unique_ptr<b200vs_scan> st(new b200vs_scan());
+    st->flat = make_flat(metric, dim, p);
+    st->nq = nq; st->k = k;
+    if (sp) {
+      st->has_sp = true; st->sp = *sp;
+      if (sp->sorted_ids && sp->n_ids > 0) st->allow.assign(sp->sorted_ids, sp->sorted_ids + sp->n_ids);
+      st->sp.sorted_ids = sp->sorted_ids ? st->allow.data() : nullptr;
+    }
+    B200VS_CUDA(cudaSetDevice(device));
+    B200VS_CUDA(cudaStreamCreateWithFlags(&st->s, cudaStreamNonBlocking));
+    const size_t nk = (size_t)nq * k;
+    st->q.reserve((size_t)nq * dim, 0, st->s);
+    st->parts_d.reserve(2 * nk, 0, st->s); st->parts_i.reserve(2 * nk, 0, st->s);
+    st->out_d.reserve(nk, 0, st->s); st->out_i.reserve(nk, 0, st->s);
+    B200VS_CUDA(cudaMemcpyAsync(st->q.p, xq, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, st->s));
+    B200VS_CUDA(cudaMemsetAsync(st->parts_d.p, 0, 2 * nk * 4, st->s));
+    B200VS_CUDA(cudaMemsetAsync(st->parts_i.p, 0xFF, 2 * nk * 8, st->s));  // id -1 = empty slot
+    B200VS_CUDA(cudaStreamSynchronize(st->s));
+    *out = st.release();
+    return B200VS_OK;
+  });
+}
+
+int b200vs_scan_push(b200vs_scan* st, int64_t n, const float* x, const int64_t* ids) {
+  return guarded([&]() -> int {
+    if (!st || !st->flat) fail(B200VS_EILLEGAL_PARAMETERS, "null scan handle");
+    if (n <= 0) return B200VS_OK;
+    if (!x || !ids) fail(B200VS_EILLEGAL_PARAMETERS, "null tile");
+    IndexBase* ix = st->flat;
+    const size_t nk = (size_t)st->nq * st->k;
+    if (st->pushed > 0) ix->clear();
+    ix->add(n, x, ids, false);  // one temporary Flat index per tile, as the reference builds (vector_reader.cc:1937-1946)
+    {
+      std::shared_lock<std::shared_mutex> rl(ix->rw);
+      ix->set_device();
+      LaneGuard lane(ix, st->s);
+      ix->reset_stats();
+      SearchCtx sc = make_ctx(ix, st->has_sp ? &st->sp : nullptr, st->s);
+      ix->search_dev(st->nq, st->q.p, st->k, sc, st->parts_d.p + nk, st->parts_i.p + nk, st->s);
+    }
+    // running top-k <- merge(running, tile): the reference's per-query priority queues (:1956-1971)
+    launch_merge_api(2, st->nq, st->k, st->parts_d.p, st->parts_i.p, st->out_d.p, st->out_i.p, st->s);
+    B200VS_CUDA(cudaMemcpyAsync(st->parts_d.p, st->out_d.p, nk * 4, cudaMemcpyDeviceToDevice, st->s));
+    B200VS_CUDA(cudaMemcpyAsync(st->parts_i.p, st->out_i.p, nk * 8, cudaMemcpyDeviceToDevice, st->s));
+    B200VS_CUDA(cudaStreamSynchronize(st->s));  // the next push rewrites the tile index
+    st->pushed += n;
+    return B200VS_OK;
+  });
+}
+
+int b200vs_scan_finish(b200vs_scan* st, float* out_dist, int64_t* out_ids) {
+  const int rc = guarded([&]() -> int {
+    if (!st || !st->flat) fail(B200VS_EILLEGAL_PARAMETERS, "null scan handle");
+    if (!out_dist || !out_ids) fail(B200VS_EILLEGAL_PARAMETERS, "null output");
+    B200VS_CUDA(cudaSetDevice(st->flat->device));
+    const size_t nk = (size_t)st->nq * st->k;
+    B200VS_CUDA(cudaMemcpyAsync(out_dist, st->parts_d.p, nk * 4, cudaMemcpyDeviceToHost, st->s));
+    B200VS_CUDA(cudaMemcpyAsync(out_ids, st->parts_i.p, nk * 8, cudaMemcpyDeviceToHost, st->s));
+    B200VS_CUDA(cudaStreamSynchronize(st->s));
+    return B200VS_OK;
+  });
+  delete st;
+  return rc;
+}
+
+void b200vs_scan_abort(b200vs_scan* st) { delete st; }
 
 int b200vs_last_phase_times(b200vs_index* h, float ms[16]) {
   return guarded([&]() -> int {

@@ -287,6 +287,17 @@ struct FlatIndex : IndexBase {
     compact_if_needed();
   }
 
+  // streaming brute-force scan (b200vs_scan_*): the tile index is emptied between tiles, buffers are kept
+  void clear() override {
+    std::unique_lock<std::shared_mutex> wl(rw);
+    std::lock_guard<std::mutex> gl(gpu_mu);
+    set_device();
+    quiesce();
+    rows = 0; ndeleted = 0; max_norm = 0.f;
+    h_ids.clear(); id2row.clear();
+    publish_len();
+  }
+
   // VectorIndexFlat::Delete, vector_index_flat.cc:171-203: unknown ids are ignored (only ids present in
   // rev_map are handed to remove_ids).
   int64_t remove(int64_t n, const int64_t* del) override {

@@ -171,6 +171,7 @@ struct IndexBase {
   virtual int64_t get_state(void* blob, size_t cap) { (void)blob; (void)cap; return 0; }
   virtual void add(int64_t n, const float* x, const int64_t* ids, bool upsert) = 0;
   virtual int64_t remove(int64_t n, const int64_t* ids) = 0;
+  virtual void clear() { fail(B200VS_EVECTOR_NOT_SUPPORT, "clear is only implemented for FLAT"); }  // drop every row, keep the buffers
   // device-pointer search on stream s; scratch already reset; q is RAW (normalise inside for cosine)
   virtual void search_dev(int64_t nq, const float* xq, int k, const SearchCtx& sc, float* out_dist, long long* out_ids,
                           cudaStream_t s) = 0;
@@ -267,6 +268,8 @@ void launch_move_rows(const float* svecs, const long long* sids, const float* sn
 void launch_set_ids(long long* ids, const long long* slots, int64_t n, long long value, cudaStream_t s);
 void launch_iota(long long* p, int64_t n, cudaStream_t s);
 void launch_negate(float* p, int64_t n, cudaStream_t s);
+// out[i*nr + j] = L2 ? ||a_i - b_j||^2 : 1 - <a_i, b_j>, reference summation order (VectorCalcDistance)
+void launch_pair_distance(bool l2, const float* a, int64_t nl, const float* b, int64_t nr, int d, float* out, cudaStream_t s);
 void launch_merge_api(int nparts, int64_t nq, int k, const float* pd, const long long* pi, float* od, long long* oi,
                       cudaStream_t s);
 

@@ -22,7 +22,8 @@ ABI_SYMBOLS = [
     "b200vs_create", "b200vs_destroy", "b200vs_train", "b200vs_set_trained_state", "b200vs_get_trained_state",
     "b200vs_add_with_ids", "b200vs_remove_ids", "b200vs_search", "b200vs_search_device", "b200vs_coarse_device", "b200vs_search_probes_device", "b200vs_range_search",
     "b200vs_count", "b200vs_deleted_count", "b200vs_memory_size", "b200vs_is_trained", "b200vs_dimension",
-    "b200vs_save", "b200vs_load", "b200vs_export_lists", "b200vs_merge_topk_device", "b200vs_last_search_stats", "b200vs_last_phase_times", "b200vs_set_profiling",
+    "b200vs_save", "b200vs_load", "b200vs_export_lists", "b200vs_merge_topk_device", "b200vs_last_search_stats", "b200vs_last_phase_times", "b200vs_calc_distance",
+    "b200vs_scan_begin", "b200vs_scan_push", "b200vs_scan_finish", "b200vs_scan_abort", "b200vs_set_profiling",
     "b200vs_last_error", "b200vs_version",
 ]
 
@@ -85,6 +86,12 @@ def lib():
     L.b200vs_merge_topk_device.argtypes = [i32, i32, i64, i32, vp, vp, vp, vp, vp]
     L.b200vs_last_search_stats.argtypes = [vp, ctypes.POINTER(i64 * 8)]
     L.b200vs_last_phase_times.argtypes = [vp, ctypes.POINTER(ctypes.c_float * 16)]
+    L.b200vs_calc_distance.argtypes = [i32, i32, ctypes.c_int, i32, i64, vp, i64, vp, vp, vp, vp]
+    L.b200vs_scan_begin.argtypes = [i32, ctypes.c_int, i32, i64, vp, i32, ctypes.POINTER(SearchParams), ctypes.POINTER(vp)]
+    L.b200vs_scan_push.argtypes = [vp, i64, vp, vp]
+    L.b200vs_scan_finish.argtypes = [vp, vp, vp]
+    L.b200vs_scan_abort.argtypes = [vp]
+    L.b200vs_scan_abort.restype = None
     L.b200vs_set_profiling.argtypes = [vp, ctypes.c_int]
     L.b200vs_last_error.restype = ctypes.c_char_p
     L.b200vs_version.restype = ctypes.c_char_p
@@ -276,6 +283,50 @@ def ivf_state_blob(centroids, metric):
 
 def merge_topk_device(device, nparts, nq, k, parts_dist_ptr, parts_ids_ptr, out_dist_ptr, out_ids_ptr, stream=None):
     _check(lib().b200vs_merge_topk_device(device, nparts, nq, k, parts_dist_ptr, parts_ids_ptr, out_dist_ptr, out_ids_ptr, stream))
+
+
+ALGORITHM_FAISS, ALGORITHM_HNSWLIB = 1, 2
+
+
+def calc_distance(algorithm, metric, left, right, return_normalized=False, device=0):
+    """Pairwise distance matrix [nl, nr] (VectorCalcDistance); optionally the (normalised) operands as well."""
+    left, right = _f32(left), _f32(right)
+    nl, nr = left.shape[0], right.shape[0]
+    d = left.shape[1] if left.ndim == 2 else 0
+    out = np.zeros((nl, nr), dtype=np.float32)
+    lo = np.zeros_like(left) if return_normalized else None
+    ro = np.zeros_like(right) if return_normalized else None
+    _check(lib().b200vs_calc_distance(device, algorithm, metric, d, nl, left.ctypes.data if left.size else None, nr,
+                                      right.ctypes.data if right.size else None, out.ctypes.data if out.size else None,
+                                      lo.ctypes.data if lo is not None and lo.size else None, ro.ctypes.data if ro is not None and ro.size else None))
+    return (out, lo, ro) if return_normalized else out
+
+
+class BruteForceScan:
+    """Streaming brute-force top-k over tiles of vectors that are not in an index (VectorReader::BruteForceSearch)."""
+
+    def __init__(self, metric, dim, xq, k, device=0, **kw):
+        xq = _f32(xq)
+        self.nq, self.k = xq.shape[0], k
+        sp, self._keep = make_search_params(**kw)
+        self.h = ctypes.c_void_p()
+        _check(lib().b200vs_scan_begin(device, metric, dim, self.nq, xq.ctypes.data if xq.size else None, k, ctypes.byref(sp), ctypes.byref(self.h)))
+
+    def push(self, x, ids):
+        x, ids = _f32(x), _i64(ids)
+        _check(lib().b200vs_scan_push(self.h, ids.size, x.ctypes.data if x.size else None, ids.ctypes.data if ids.size else None))
+
+    def finish(self):
+        D = np.zeros((self.nq, self.k), dtype=np.float32)
+        I = np.full((self.nq, self.k), -1, dtype=np.int64)
+        h, self.h = self.h, None
+        _check(lib().b200vs_scan_finish(h, D.ctypes.data, I.ctypes.data))
+        return D, I
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().b200vs_scan_abort(self.h)
+            self.h = None
 
 
 def ivfpq_state_blob(centroids, codebooks, metric):

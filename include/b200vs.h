@@ -145,6 +145,30 @@ int b200vs_coarse_device(b200vs_index* idx, int64_t nq, const float* xq_dev, int
 int b200vs_search_probes_device(b200vs_index* idx, int64_t nq, const float* xq_dev, int32_t k, const int64_t* probes_dev, int32_t nprobe,
                                 const b200vs_search_params* sp, float* out_dist_dev, int64_t* out_ids_dev, void* stream);
 
+/* Pairwise distance matrix, the UtilService path UtilServiceImpl::VectorCalcDistance (src/server/util_service.cc:45-92)
+ * -> VectorIndexUtils::CalcDistanceEntry / CalcDistanceCore (src/vector/vector_index_utils.cc:48-124).  Host pointers,
+ * row-major left [nl, dim], right [nr, dim]; out [nl, nr]: L2 -> squared L2, IP -> 1 - ip, COSINE -> 1 - ip of the
+ * normalised copies (algorithm FAISS: NormalizeVectorForFaiss :480-491; HNSWLIB: NormalizeVectorForHnsw :493-500).
+ * left_out / right_out (nullable) = what is_return_normlize returns: the normalised copies for COSINE, else the inputs. */
+enum { B200VS_ALGORITHM_FAISS = 1, B200VS_ALGORITHM_HNSWLIB = 2 };  /* pb::index::AlgorithmType */
+int b200vs_calc_distance(int32_t device, int32_t algorithm, b200vs_metric metric, int32_t dim, int64_t nl, const float* left,
+                         int64_t nr, const float* right, float* out, float* left_out, float* right_out);
+
+/* Streaming brute-force search over vectors that are NOT in an index: VectorReader::BruteForceSearch
+ * (src/vector/vector_reader.cc:1873-2048), which scans the region's vector column family, builds a temporary Flat
+ * index per FLAGS_vector_index_bruteforce_batch_count vectors, searches it and keeps per-query top-k heaps.
+ *   scan_begin : the queries (host, raw; COSINE is normalised inside), k, optional id filters (copied);
+ *   scan_push  : one tile of scanned vectors + ids (host; any size, ids unique inside a tile) -> tile top-k on the GPU,
+ *                merged into the running top-k with the (distance, id) rule;
+ *   scan_finish: running top-k -> out_dist / out_ids [nq, k] (API distances ascending, -1 padded); frees the handle.
+ * The result equals one Flat search over the concatenation of all tiles. */
+typedef struct b200vs_scan b200vs_scan;
+int b200vs_scan_begin(int32_t device, b200vs_metric metric, int32_t dim, int64_t nq, const float* xq, int32_t k,
+                      const b200vs_search_params* sp, b200vs_scan** out);
+int b200vs_scan_push(b200vs_scan* scan, int64_t n, const float* x, const int64_t* ids);
+int b200vs_scan_finish(b200vs_scan* scan, float* out_dist, int64_t* out_ids);
+void b200vs_scan_abort(b200vs_scan* scan);
+
 /* Counters of the last search on this index: [0] kernels launched, [1] queries served by the tensor-core
  * candidate pass, [2] queries that failed certification and were re-run on the exact path; with profiling on
  * (b200vs_set_profiling) also [3] device time of the dominant list-scan kernel in ns (CUDA events on the launch

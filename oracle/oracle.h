@@ -105,6 +105,15 @@ int oracle_hnsw_export(oracle_hnsw*, void* blob, int64_t len);
 /* harness utility: multi-threaded first-touch copy (NUMA-spread pages for the timed CPU baseline) */
 void oracle_parallel_copy(void* dst, const void* src, size_t bytes, int nthreads);
 
+/* ---- pairwise distance matrix: VectorIndexUtils::CalcDistanceEntry / CalcDistanceCore
+ * (src/vector/vector_index_utils.cc:48-124) with the per-pair functions DoCalc{L2,Ip,Cosine}DistanceBy{Faiss,Hnswlib}
+ * (:193-419).  algorithm 1 = ALGORITHM_FAISS, 2 = ALGORITHM_HNSWLIB.  out[i*nr + j] = distance(left i, right j):
+ * L2 -> squared L2; IP -> 1 - ip; COSINE -> 1 - ip of the normalised copies (faiss flavour: NormalizeVectorForFaiss
+ * :480-491; hnswlib flavour: NormalizeVectorForHnsw :493-500).  left_out / right_out (nullable, [nl,d] / [nr,d]) receive
+ * what is_return_normlize returns: the normalised copies for COSINE, the inputs otherwise. */
+int oracle_calc_distance(int algorithm, int metric, int32_t d, int64_t nl, const float* left, int64_t nr,
+                         const float* right, float* out, float* left_out, float* right_out);
+
 const char* oracle_version(void);
 
 #ifdef __cplusplus

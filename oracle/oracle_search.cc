@@ -215,4 +215,35 @@ int oracle_ivfflat_search(int metric, int32_t d, int32_t nlist, const float* cen
   return 0;
 }
 
+// Pairwise distance matrix: CalcDistanceEntry -> CalcDistanceCore (src/vector/vector_index_utils.cc:48-124), one
+// DoCalc*Distance call per (left, right) pair (:193-419).  faiss::VectorDistance<METRIC_L2 / INNER_PRODUCT> and
+// the hnswlib space functions are the hooked fvec_L2sqr / fvec_inner_product (src/vector/vector_index.cc:153-185);
+// hnswlib's InnerProductSpace already returns 1 - ip, the faiss flavour subtracts explicitly (:262) - same value.
+int oracle_calc_distance(int algorithm, int metric, int32_t d, int64_t nl, const float* left, int64_t nr,
+                         const float* right, float* out, float* left_out, float* right_out) {
+  if ((algorithm != 1 && algorithm != 2) || (metric != ORACLE_L2 && metric != ORACLE_IP && metric != ORACLE_COSINE)) return -1;
+  if (d <= 0 || nl < 0 || nr < 0) return -1;
+  std::vector<float> ln((size_t)nl * d), rn((size_t)nr * d);
+  auto prep = [&](const float* src, float* dst, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) {
+      const float* s = src + i * (int64_t)d;
+      float* t = dst + i * (int64_t)d;
+      if (metric != ORACLE_COSINE) { std::memcpy(t, s, (size_t)d * 4); continue; }
+      if (algorithm == 1) { std::memcpy(t, s, (size_t)d * 4); oracle_normalize_faiss(t, d); }  // :283-284
+      else oracle_normalize_hnsw(s, d, t);                                                        // :407-413
+    }
+  };
+  prep(left, ln.data(), nl);
+  prep(right, rn.data(), nr);
+  for (int64_t i = 0; i < nl; ++i)
+    for (int64_t j = 0; j < nr; ++j) {
+      const float* a = ln.data() + i * (int64_t)d;
+      const float* b = rn.data() + j * (int64_t)d;
+      out[i * nr + j] = metric == ORACLE_L2 ? oracle_fvec_L2sqr(a, b, d) : 1.0f - oracle_fvec_inner_product(a, b, d);
+    }
+  if (left_out) std::memcpy(left_out, ln.data(), ln.size() * 4);
+  if (right_out) std::memcpy(right_out, rn.data(), rn.size() * 4);
+  return 0;
+}
+
 }  // extern "C"

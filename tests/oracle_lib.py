@@ -52,6 +52,7 @@ class Oracle:
         L.oracle_pq_encode.argtypes = [i32, i32, i32, vp, i64, vp, ctypes.c_int, vp]
         L.oracle_ivfpq_encode.argtypes = [i32, i32, i32, vp, i32, vp, i64, vp, vp, ctypes.c_int, vp]
         L.oracle_ivfpq_search.argtypes = [ctypes.c_int, i32, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp, i32, i32, fp, ctypes.c_int, vp, vp]
+        L.oracle_calc_distance.argtypes = [ctypes.c_int, ctypes.c_int, i32, i64, vp, i64, vp, vp, vp, vp]
         L.oracle_hnsw_create.argtypes = [ctypes.c_int, i32, i64, i32, i32, i64]
         L.oracle_hnsw_create.restype = vp
         L.oracle_hnsw_destroy.argtypes = [vp]
@@ -113,6 +114,16 @@ class Oracle:
         return f, keep
 
     # ---- searches ----
+    def calc_distance(self, algorithm, metric, left, right):
+        """(distances [nl, nr], left_out, right_out) of VectorIndexUtils::CalcDistanceEntry."""
+        left, right = _f32(left), _f32(right)
+        nl, nr, d = left.shape[0], right.shape[0], left.shape[1]
+        out = np.zeros((nl, nr), np.float32)
+        lo, ro = np.zeros_like(left), np.zeros_like(right)
+        rc = self.L.oracle_calc_distance(algorithm, metric, d, nl, left.ctypes.data, nr, right.ctypes.data, out.ctypes.data, lo.ctypes.data, ro.ctypes.data)
+        assert rc == 0
+        return out, lo, ro
+
     def flat_search(self, metric, xb, ids, xq, k, nthreads=1, **filt):
         xb, ids, xq = _f32(xb), _i64(ids), _f32(xq)
         n, d = xb.shape if xb.ndim == 2 else (0, xq.shape[1])

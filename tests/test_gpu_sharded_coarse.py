@@ -119,6 +119,44 @@ def test_coarse_split_by_queries_equals_plain_search():
     assert np.array_equal(sc.cpu().numpy()[:64].view(np.uint32), cd.view(np.uint32))
 
 
+@pytest.mark.parametrize("metric", [b200vs.L2, b200vs.IP])
+@pytest.mark.parametrize("nlist", [2048, 4096, 8192, 10000])
+def test_coarse_large_tables_match_oracle(metric, nlist):
+    """Every register-select width (8 / 16 / 32 keys per thread) and the generic path above 8192 centroids, on a
+    trained state loaded from outside (random centroids, duplicates included so exact ties occur)."""
+    require_gpu()
+    import torch
+    d, nq, nprobe = 64, 96, 48
+    rng = np.random.default_rng(nlist)
+    cent = rng.random((nlist, d), dtype=np.float32)
+    cent[5] = cent[4]
+    cent[nlist - 1] = cent[7]
+    ix = b200vs.Index(b200vs.IVF_FLAT, metric, d, nlist=nlist)
+    ix.set_trained_state(b200vs.ivf_state_blob(cent, metric))
+    xq = rng.random((nq, d), dtype=np.float32)
+    xq[0] = cent[4]
+    q = torch.from_numpy(xq).cuda()
+    sc = torch.empty((nq, nprobe), dtype=torch.float32, device="cuda")
+    pl = torch.empty((nq, nprobe), dtype=torch.int64, device="cuda")
+    ix.coarse_device(nq, q.data_ptr(), nprobe, 0, nlist, sc.data_ptr(), pl.data_ptr())
+    o = oracle_lib.load()
+    om = oracle_lib.L2 if metric == b200vs.L2 else oracle_lib.IP
+    cd, ci = o.flat_search(om, cent, np.arange(nlist, dtype=np.int64), xq, nprobe)
+    assert np.array_equal(pl.cpu().numpy(), ci)
+    if metric == b200vs.L2:
+        assert np.array_equal(sc.cpu().numpy().view(np.uint32), cd.view(np.uint32))
+    # the probe-table flavour (set mode) must select the same SET of lists
+    xb = rng.random((4000, d), dtype=np.float32)
+    ix.add(xb, np.arange(4000, dtype=np.int64))
+    wd, wi = ix.search(xq, 10, nprobe=nprobe)
+    od = torch.empty((nq, 10), dtype=torch.float32, device="cuda")
+    oi = torch.empty((nq, 10), dtype=torch.int64, device="cuda")
+    sp, _keep = b200vs.make_search_params(nprobe=nprobe)
+    ix.search_probes_device(nq, q.data_ptr(), 10, pl.data_ptr(), nprobe, od.data_ptr(), oi.data_ptr(), sp=sp)
+    assert np.array_equal(oi.cpu().numpy(), wi)
+    assert np.array_equal(od.cpu().numpy().view(np.uint32), wd.view(np.uint32))
+
+
 def test_coarse_device_rejects_bad_range():
     require_gpu()
     import torch

@@ -164,3 +164,31 @@ def test_hnsw_recall_and_contract(oracle, metric):
     blob = h.export()
     hdr = blob[:64].view(np.int64)
     assert hdr[0] == 0x57534E48 and hdr[1] == n and hdr[2] == d
+
+
+@pytest.mark.parametrize("algorithm", [1, 2])
+def test_calc_distance_pinned_to_reference_kernels(oracle, algorithm):
+    """oracle_calc_distance (vector_index_utils.cc:48-124): every entry is the hooked kernel's value — checked against
+    the reference's own src/simd objects (oracle/_ref) when they are built — and the two normalisers differ."""
+    rng = np.random.default_rng(3)
+    left = rng.random((5, 77), dtype=np.float32)
+    right = rng.random((6, 77), dtype=np.float32) * 2 - 0.5
+    ref = oracle_lib.load_ref()
+    d2, lo, ro = oracle.calc_distance(algorithm, oracle_lib.L2, left, right)
+    ip, _, _ = oracle.calc_distance(algorithm, oracle_lib.IP, left, right)
+    assert np.array_equal(lo, left) and np.array_equal(ro, right)
+    for i in range(5):
+        for j in range(6):
+            if ref is not None:
+                assert d2[i, j] == ref.ref_fvec_L2sqr_avx512(left[i].ctypes.data, right[j].ctypes.data, 77)
+                assert ip[i, j] == np.float32(1.0) - np.float32(ref.ref_fvec_inner_product_avx512(left[i].ctypes.data, right[j].ctypes.data, 77))
+            assert abs(d2[i, j] - float(((left[i].astype(np.float64) - right[j]) ** 2).sum())) < 1e-3
+    cs, ln, rn = oracle.calc_distance(algorithm, oracle_lib.COSINE, left, right)
+    want_l = oracle.normalize_faiss(left) if algorithm == 1 else oracle.normalize_hnsw(left)
+    assert np.array_equal(ln, want_l)
+    cos64 = 1 - (left.astype(np.float64) @ right.T.astype(np.float64)) / np.outer(np.linalg.norm(left.astype(np.float64), axis=1), np.linalg.norm(right.astype(np.float64), axis=1))
+    assert np.abs(cs - cos64).max() < 1e-5
+    # hand-checkable: (1,2,3) vs (4,6,8)
+    a, b = np.array([[1, 2, 3]], np.float32), np.array([[4, 6, 8]], np.float32)
+    assert oracle.calc_distance(algorithm, oracle_lib.L2, a, b)[0][0, 0] == 50.0
+    assert oracle.calc_distance(algorithm, oracle_lib.IP, a, b)[0][0, 0] == -39.0
