@@ -2,6 +2,8 @@
 // (test/unit_test/vector/test_vector_index_{flat,ivf_flat,hnsw,flat_search_param}.cc): same fixtures (default-seeded
 // std::mt19937, row[0] += i/1000.), same asserted contract (status codes, result counts, filter containment,
 // self-match at rank 0).  Needs a GPU; run by tests/test_gpu_plugin_cpp.py.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -160,10 +162,69 @@ static void test_hnsw() {
   EXPECT(!ix->IsExceedsMaxElements(10) && ix->IsExceedsMaxElements(100000));
 }
 
+static void test_calc_distance() {  // the contract of VectorIndexUtils::CalcDistanceEntry (vector_index_utils.cc:48-124)
+  auto vec = [](std::initializer_list<float> v) { pb::common::Vector x; for (float f : v) x.add_float_values(f); return x; };
+  std::vector<pb::common::Vector> left{vec({1, 2, 3})}, right{vec({4, 6, 8}), vec({1, 2, 3})}, rl, rr;
+  std::vector<std::vector<float>> dist;
+  EXPECT(VectorIndexB200Utils::CalcDistance(1, pb::common::METRIC_TYPE_L2, left, right, false, dist, rl, rr).ok());
+  EXPECT(dist.size() == 1 && dist[0].size() == 2 && dist[0][0] == 50.0f && dist[0][1] == 0.0f);
+  EXPECT(rl.empty() && rr.empty());
+  EXPECT(VectorIndexB200Utils::CalcDistance(2, pb::common::METRIC_TYPE_INNER_PRODUCT, left, right, true, dist, rl, rr).ok());
+  EXPECT(dist[0][0] == -39.0f && dist[0][1] == -13.0f);  // 1 - ip
+  EXPECT(rl.size() == 1 && rr.size() == 2 && rl[0].float_values() == left[0].float_values() && rl[0].dimension() == 3);
+  for (int alg = 1; alg <= 2; ++alg) {
+    EXPECT(VectorIndexB200Utils::CalcDistance(alg, pb::common::METRIC_TYPE_COSINE, left, right, true, dist, rl, rr).ok());
+    EXPECT(std::abs(dist[0][1]) < 1e-6f && std::abs(dist[0][0] - 0.0074f) < 1e-3f);
+    float n2 = 0;
+    for (float f : rr[0].float_values()) n2 += f * f;
+    EXPECT(std::abs(n2 - 1.0f) < 1e-5f);  // normalised operands are returned
+  }
+  EXPECT(VectorIndexB200Utils::CalcDistance(0, pb::common::METRIC_TYPE_L2, left, right, false, dist, rl, rr).error_code() == pb::error::EILLEGAL_PARAMTETERS);
+  EXPECT(VectorIndexB200Utils::CalcDistance(1, pb::common::METRIC_TYPE_NONE, left, right, false, dist, rl, rr).error_code() == pb::error::EILLEGAL_PARAMTETERS);
+}
+
+static void test_bruteforce_scanner() {  // VectorReader::BruteForceSearch's batch loop (vector_reader.cc:1873-2048) vs one Flat index
+  const int n = 5000, d = 64, nq = 7;
+  const uint32_t topk = 5;
+  const auto x = fixture(n, d);
+  const auto rows = to_pb(x, n, d, 1);
+  std::vector<pb::common::VectorWithId> queries(rows.begin(), rows.begin() + nq);
+  auto flat = make(pb::common::VECTOR_INDEX_TYPE_FLAT, pb::common::METRIC_TYPE_L2, d);
+  EXPECT(flat->Add(rows).ok());
+  std::vector<pb::index::VectorWithDistanceResult> want, got;
+  EXPECT(flat->Search(queries, topk, {}, false, pb::common::VectorSearchParameter(), want).ok());
+  BruteForceScannerB200 scanner(pb::common::METRIC_TYPE_L2, d, queries, topk);
+  for (int a = 0; a < n; a += 2048) {  // FLAGS_vector_index_bruteforce_batch_count
+    std::vector<pb::common::VectorWithId> batch(rows.begin() + a, rows.begin() + std::min(n, a + 2048));
+    EXPECT(scanner.Push(batch).ok());
+  }
+  EXPECT(scanner.Finish(got).ok());
+  EXPECT(got.size() == (size_t)nq);
+  for (int q = 0; q < nq && q < (int)got.size(); ++q) {
+    EXPECT(got[q].vector_with_distances_size() == (int)topk);
+    EXPECT(got[q].vector_with_distances(0).vector_with_id().id() == q + 1);  // self match at rank 0
+    for (int i = 0; i < got[q].vector_with_distances_size(); ++i) {
+      EXPECT(got[q].vector_with_distances(i).vector_with_id().id() == want[q].vector_with_distances(i).vector_with_id().id());
+      EXPECT(got[q].vector_with_distances(i).distance() == want[q].vector_with_distances(i).distance());
+    }
+  }
+  std::vector<pb::common::VectorWithId> bad(1);
+  bad[0].set_id(1);
+  bad[0].mutable_vector()->set_dimension(3);
+  for (int j = 0; j < 3; ++j) bad[0].mutable_vector()->add_float_values(0.f);
+  BruteForceScannerB200 s2(pb::common::METRIC_TYPE_L2, d, queries, topk);
+  EXPECT(s2.Push(bad).error_code() == pb::error::EVECTOR_INVALID);
+  std::vector<pb::index::VectorWithDistanceResult> none;
+  BruteForceScannerB200 s3(pb::common::METRIC_TYPE_L2, d, queries, topk);
+  EXPECT(s3.Finish(none).ok() && none.size() == (size_t)nq && none[0].vector_with_distances_size() == 0);  // empty region: no hits
+}
+
 int main() {
   test_flat();
   test_ivf_flat();
   test_hnsw();
+  test_calc_distance();
+  test_bruteforce_scanner();
   printf(g_fail ? "PLUGIN TESTS FAILED: %d\n" : "PLUGIN TESTS OK%.0d\n", g_fail);
   return g_fail ? 1 : 0;
 }

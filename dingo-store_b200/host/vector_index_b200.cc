@@ -271,4 +271,107 @@ bool VectorIndexB200::NeedTrain() {
 bool VectorIndexB200::IsTrained() { return index_ && b200vs_is_trained(index_) != 0; }
 bool VectorIndexB200::NeedToSave(int64_t last_save_log_behind) { return SupportSave() && last_save_log_behind > 10000; }  // flat.cc:515-531
 
+namespace {
+butil::Status AbiStatus(int rc) {
+  if (rc == B200VS_OK) return butil::Status::OK();
+  pb::error::Errno e = pb::error::EINTERNAL;
+  if (rc == B200VS_EILLEGAL_PARAMETERS) e = pb::error::EILLEGAL_PARAMTETERS;
+  else if (rc == B200VS_EVECTOR_INVALID) e = pb::error::EVECTOR_INVALID;
+  else if (rc == B200VS_EVECTOR_ID_DUPLICATED) e = pb::error::EVECTOR_ID_DUPLICATED;
+  else if (rc == B200VS_EVECTOR_NOT_SUPPORT) e = pb::error::EVECTOR_NOT_SUPPORT;
+  return butil::Status(e, b200vs_last_error());
+}
+b200vs_metric AbiMetric(pb::common::MetricType m) {
+  return m == pb::common::METRIC_TYPE_INNER_PRODUCT ? B200VS_IP : m == pb::common::METRIC_TYPE_COSINE ? B200VS_COSINE : B200VS_L2;
+}
+}  // namespace
+
+butil::Status VectorIndexB200Utils::CalcDistance(int algorithm_type, pb::common::MetricType metric_type,
+                                                 const std::vector<pb::common::Vector>& op_left_vectors,
+                                                 const std::vector<pb::common::Vector>& op_right_vectors, bool is_return_normlize,
+                                                 std::vector<std::vector<float>>& distances,
+                                                 std::vector<pb::common::Vector>& result_op_left_vectors,
+                                                 std::vector<pb::common::Vector>& result_op_right_vectors, int device) {
+  if (algorithm_type != B200VS_ALGORITHM_FAISS && algorithm_type != B200VS_ALGORITHM_HNSWLIB)
+    return butil::Status(pb::error::EILLEGAL_PARAMTETERS, "invalid algorithm type : ALGORITHM_NONE");     // utils.cc:70-76
+  if (metric_type != pb::common::METRIC_TYPE_L2 && metric_type != pb::common::METRIC_TYPE_INNER_PRODUCT && metric_type != pb::common::METRIC_TYPE_COSINE)
+    return butil::Status(pb::error::EILLEGAL_PARAMTETERS, "invalid metric_type type : METRIC_TYPE_NONE");  // utils.cc:151-157
+  distances.clear();
+  distances.resize(op_left_vectors.size());  // CalcDistanceCore, utils.cc:86-88
+  if (op_left_vectors.empty() || op_right_vectors.empty()) return butil::Status::OK();
+  const size_t d = op_left_vectors[0].float_values().size();
+  for (const auto& v : op_left_vectors) if (v.float_values().size() != d) return butil::Status(pb::error::EILLEGAL_PARAMTETERS, "op_left_vectors dimension not match");
+  for (const auto& v : op_right_vectors) if (v.float_values().size() != d) return butil::Status(pb::error::EILLEGAL_PARAMTETERS, "op_right_vectors dimension not match");
+  const size_t nl = op_left_vectors.size(), nr = op_right_vectors.size();
+  std::vector<float> left(nl * d), right(nr * d), out(nl * nr), lo, ro;
+  for (size_t i = 0; i < nl; ++i) memcpy(left.data() + i * d, op_left_vectors[i].float_values().data(), d * sizeof(float));
+  for (size_t i = 0; i < nr; ++i) memcpy(right.data() + i * d, op_right_vectors[i].float_values().data(), d * sizeof(float));
+  if (is_return_normlize) { lo.resize(nl * d); ro.resize(nr * d); }
+  const int rc = b200vs_calc_distance(device, algorithm_type, AbiMetric(metric_type), (int32_t)d, (int64_t)nl, left.data(), (int64_t)nr, right.data(),
+                                      out.data(), is_return_normlize ? lo.data() : nullptr, is_return_normlize ? ro.data() : nullptr);
+  if (rc != B200VS_OK) return AbiStatus(rc);
+  for (size_t i = 0; i < nl; ++i) distances[i].assign(out.begin() + i * nr, out.begin() + (i + 1) * nr);
+  if (is_return_normlize) {  // ResultOpVectorAssignment, utils.cc:421-426
+    auto fill = [&](std::vector<pb::common::Vector>& dst, const std::vector<float>& src, size_t n) {
+      dst.clear();
+      dst.resize(n);
+      for (size_t i = 0; i < n; ++i) {
+        dst[i].mutable_float_values()->assign(src.begin() + i * d, src.begin() + (i + 1) * d);
+        dst[i].set_dimension((int32_t)d);
+        dst[i].set_value_type(pb::common::ValueType::FLOAT);
+      }
+    };
+    fill(result_op_left_vectors, lo, nl);
+    fill(result_op_right_vectors, ro, nr);
+  }
+  return butil::Status::OK();
+}
+
+BruteForceScannerB200::BruteForceScannerB200(pb::common::MetricType metric_type, int32_t dimension,
+                                             const std::vector<pb::common::VectorWithId>& vector_with_ids, uint32_t topk, int device)
+    : metric_type_(metric_type), dimension_(dimension), nq_(vector_with_ids.size()), topk_(topk) {
+  if (dimension <= 0) { init_status_ = butil::Status(pb::error::EVECTOR_INVALID, "vector index dimension is invalid"); return; }  // reader.cc:1889-1894
+  if (vector_with_ids.empty()) { init_status_ = butil::Status(pb::error::EILLEGAL_PARAMTETERS, "vector_with_ids is empty"); return; }
+  init_status_ = CheckVectorDimension(vector_with_ids, dimension);
+  if (!init_status_.ok() || topk == 0) return;
+  const std::vector<float> x = ExtractVectorValue(vector_with_ids, dimension);
+  init_status_ = AbiStatus(b200vs_scan_begin(device, AbiMetric(metric_type), dimension, (int64_t)nq_, x.data(), (int32_t)topk, nullptr, &scan_));
+}
+BruteForceScannerB200::~BruteForceScannerB200() { if (scan_) b200vs_scan_abort(scan_); }
+
+butil::Status BruteForceScannerB200::Push(const std::vector<pb::common::VectorWithId>& batch) {
+  if (!init_status_.ok()) return init_status_;
+  if (batch.empty() || topk_ == 0) return butil::Status::OK();
+  auto status = CheckVectorDimension(batch, dimension_);
+  if (!status.ok()) return status;
+  std::vector<int64_t> ids(batch.size());
+  for (size_t i = 0; i < batch.size(); ++i) ids[i] = batch[i].id();
+  const std::vector<float> x = ExtractVectorValue(batch, dimension_);
+  return AbiStatus(b200vs_scan_push(scan_, (int64_t)batch.size(), x.data(), ids.data()));
+}
+
+butil::Status BruteForceScannerB200::Finish(std::vector<pb::index::VectorWithDistanceResult>& results) {
+  if (!init_status_.ok()) return init_status_;
+  results.resize(nq_);  // reader.cc:2022
+  if (topk_ == 0) return butil::Status::OK();
+  std::vector<float> distances(nq_ * topk_, 0.0f);
+  std::vector<int64_t> labels(nq_ * topk_, -1);
+  b200vs_scan* s = scan_;
+  scan_ = nullptr;  // finish frees the handle
+  const int rc = b200vs_scan_finish(s, distances.data(), labels.data());
+  if (rc != B200VS_OK) return AbiStatus(rc);
+  for (size_t row = 0; row < nq_; ++row)
+    for (uint32_t i = 0; i < topk_; ++i) {
+      const size_t pos = row * topk_ + i;
+      if (labels[pos] < 0) continue;
+      auto* vwd = results[row].add_vector_with_distances();
+      vwd->mutable_vector_with_id()->set_id(labels[pos]);
+      vwd->mutable_vector_with_id()->mutable_vector()->set_dimension(dimension_);
+      vwd->mutable_vector_with_id()->mutable_vector()->set_value_type(pb::common::ValueType::FLOAT);
+      vwd->set_distance(distances[pos]);
+      vwd->set_metric_type(metric_type_);
+    }
+  return butil::Status::OK();
+}
+
 }  // namespace dingodb

@@ -76,4 +76,35 @@ class VectorIndexB200 : public VectorIndex {
   std::shared_mutex write_gate_;  // LockWrite/UnlockWrite of the snapshot path; reads and writes lock inside the library
 };
 
+// VectorIndexUtils::CalcDistanceEntry (src/vector/vector_index_utils.cc:48-76) over the C ABI: same operand meaning
+// (algorithm_type = pb::index::AlgorithmType: 1 FAISS, 2 HNSWLIB; metric; is_return_normlize) and the same error codes.
+class VectorIndexB200Utils {
+ public:
+  static butil::Status CalcDistance(int algorithm_type, pb::common::MetricType metric_type, const std::vector<pb::common::Vector>& op_left_vectors,
+                                    const std::vector<pb::common::Vector>& op_right_vectors, bool is_return_normlize,
+                                    std::vector<std::vector<float>>& distances, std::vector<pb::common::Vector>& result_op_left_vectors,
+                                    std::vector<pb::common::Vector>& result_op_right_vectors, int device = 0);
+};
+
+// The inner loop of VectorReader::BruteForceSearch (src/vector/vector_reader.cc:1873-2048): the caller keeps the RocksDB
+// iterator, pushes each decoded batch (FLAGS_vector_index_bruteforce_batch_count vectors) and collects the top-k at the end.
+class BruteForceScannerB200 {
+ public:
+  BruteForceScannerB200(pb::common::MetricType metric_type, int32_t dimension, const std::vector<pb::common::VectorWithId>& vector_with_ids,
+                        uint32_t topk, int device = 0);
+  ~BruteForceScannerB200();
+  BruteForceScannerB200(const BruteForceScannerB200&) = delete;
+  BruteForceScannerB200& operator=(const BruteForceScannerB200&) = delete;
+  butil::Status Push(const std::vector<pb::common::VectorWithId>& vector_with_id_batch);
+  butil::Status Finish(std::vector<pb::index::VectorWithDistanceResult>& results);  // ascending by distance, one entry per query
+
+ private:
+  b200vs_scan* scan_ = nullptr;
+  butil::Status init_status_;
+  pb::common::MetricType metric_type_;
+  int32_t dimension_;
+  size_t nq_;
+  uint32_t topk_;
+};
+
 }  // namespace dingodb
