@@ -404,6 +404,7 @@ struct IvfFlatIndex : IndexBase {
     TcView v;
     v.vecs = vecs.p; v.ids = ids.p; v.norms = norms.p; v.arena_rows = L.arena_used; v.list_off = L.d_off.p; v.list_len = L.d_len.p;
     v.nlist = nlist; v.total_chunks = L.total_chunks; v.max_chunks_per_list = L.max_chunks_per_list; v.max_norm = max_norm;
+    v.owned_frac = nlist > 0 ? (float)L.nonempty_lists / (float)nlist : 1.f;
     return v;
   }
 

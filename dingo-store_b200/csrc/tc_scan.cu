@@ -262,18 +262,19 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const TcItem I = p.items[it];
         const long long base_row = p.list_off[I.list] + I.row_begin;
         int rows = I.row_end - I.row_begin;
-        if (p.mode == 0) rows = min(rows, TC_SAMPLE);
+        if (p.mode == 0) rows = min(rows, p.sample_rows);
         const int ntiles = (rows + TC_BM - 1) / TC_BM;
         const int b_rows = I.nq <= 16 ? 16 : (I.nq <= 32 ? 32 : (I.nq <= 64 ? 64 : 128));
         const CUtensorMap* tb = I.nq <= 16 ? &tmB16 : (I.nq <= 32 ? &tmB32 : (I.nq <= 64 ? &tmB64 : &tmB128));
-        const CUtensorMap* ta = p.mode == 0 ? &tmA32 : &tmA;
-        const uint32_t bytes = (p.mode == 0 ? (uint32_t)(TC_SAMPLE * 128) : TC_A_BYTES) + (uint32_t)b_rows * 128u;
+        const bool small_a = p.mode == 0 && p.sample_rows == TC_SAMPLE;  // 32-row sample box, else the full 128-row tile
+        const CUtensorMap* ta = small_a ? &tmA32 : &tmA;
+        const uint32_t bytes = (small_a ? (uint32_t)(TC_SAMPLE * 128) : TC_A_BYTES) + (uint32_t)b_rows * 128u;
         const CUtensorMap* tbl = I.nq <= 16 ? &tmBlo16 : (I.nq <= 32 ? &tmBlo32 : (I.nq <= 64 ? &tmBlo64 : &tmBlo128));
         const int npad_b = max(16, (I.nq + 15) & ~15);
         uint32_t bytes_g = bytes;
         if (p.b_gather) {
           for (int j = 0; j < npad_b; ++j) s_brow[j] = j < I.nq ? p.pair_query[I.pair_begin + j] : 0;
-          bytes_g = (p.mode == 0 ? (uint32_t)(TC_SAMPLE * 128) : TC_A_BYTES) + (uint32_t)npad_b * 128u;
+          bytes_g = (small_a ? (uint32_t)(TC_SAMPLE * 128) : TC_A_BYTES) + (uint32_t)npad_b * 128u;
         }
         for (int t = 0; t < ntiles; ++t)
           for (int kb = 0; kb < kblocks; ++kb) {
@@ -319,7 +320,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (it < 0) break;
         const TcItem I = p.items[it];
         int rows = I.row_end - I.row_begin;
-        if (p.mode == 0) rows = min(rows, TC_SAMPLE);
+        if (p.mode == 0) rows = min(rows, p.sample_rows);
         const int ntiles = (rows + TC_BM - 1) / TC_BM;
         const uint32_t npad = (uint32_t)max(16, (I.nq + 15) & ~15);
         const uint32_t idesc = make_idesc_tf32(TC_BM, npad);
@@ -382,7 +383,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const long long list_base = p.list_off[I.list];
       int rows = I.row_end - I.row_begin;
-      if (p.mode == 0) rows = min(rows, TC_SAMPLE);
+      if (p.mode == 0) rows = min(rows, p.sample_rows);
       const int ntiles = (rows + TC_BM - 1) / TC_BM;
       const int npad = max(16, (I.nq + 15) & ~15);
       for (int t = 0; t < ntiles; ++t, ++tcount) {
@@ -422,7 +423,7 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   }
                 }
               } else if (p.mode == 0) {
-                if (ew == 0 && t == 0) p.sample[((size_t)I.sample_slot * TC_NQT + n) * TC_SAMPLE + lane] = valid ? score : TC_INF;
+                if (t == 0 && r < p.sample_rows) p.sample[((size_t)I.sample_slot * TC_NQT + n) * p.sample_rows + r] = valid ? score : TC_INF;
               } else if (inrange) {
                 float* dst = p.dense + (size_t)s_q[buf][n] * p.dense_ld + (I.row_begin + r);
                 if (p.dense_accum) *dst = *dst + score;
@@ -455,9 +456,14 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// per-query capture threshold: the k-th smallest sampled score (an upper bound of the k-th smallest score overall)
+// per-query capture threshold T.  tau = the k-th smallest sampled score bounds the k-th smallest score overall (A_k)
+// from above.  Thin samples (32 rows per span, ~1 % of the probed rows) leave tau far above A_k + 2 eps and T = tau:
+// the finish kernel certifies A_k + 2 eps <= T and sends the rare failure to the exact scan.  Dense samples (the whole
+// first tile, used when a query probes few local lists) put tau close to A_k, so T = tau + 2 eps: then
+// A_k + 2 eps <= T by construction and certification can only fail on a buffer overflow.
 // ---------------------------------------------------------------------------------------------
 __device__ uint32_t block_kth_key(const unsigned long long* keys, int n, int k);
+__device__ __forceinline__ float tc_eps(bool l2, float qnorm_sq, float max_norm, int d, bool split);
 
 constexpr int TAU_PL = 4096;  // (sample slot, column) pairs staged per query
 constexpr int TAU_SORT = 4096;  // sampled scores sorted in one shot when they fit
@@ -465,7 +471,8 @@ constexpr int TAU_SORT = 4096;  // sampled scores sorted in one shot when they f
 static __global__ void __launch_bounds__(SCAN_THREADS)
 tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos, const int* __restrict__ cnt,
               const int* __restrict__ item_off, const int* __restrict__ list_len, const TcItem* __restrict__ items, int nprobe,
-              const float* __restrict__ sample, int k, int pool_cap, float* tau) {
+              const float* __restrict__ sample, int srows, int k, int pool_cap, int l2, const float* __restrict__ qnorm,
+              float max_norm, int d, int margin, float* tau) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_np;
   const int q = blockIdx.x;
@@ -491,30 +498,30 @@ tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos,
   __syncthreads();
   const int np_all = s_np;
   const int np = min(np_all, TAU_PL);
-  const int tot = np * TC_SAMPLE;
+  const int tot = np * srows;
   if (np_all <= TAU_PL && tot <= TAU_SORT) {  // common case: radix-select the k-th smallest sampled score in shared memory
     unsigned long long* vals = reinterpret_cast<unsigned long long*>(smem + (size_t)TAU_PL * 8);
     __shared__ int s_fin;
     if (threadIdx.x == 0) s_fin = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < tot; i += blockDim.x) {
-      const int2 pr = s_pairs[i / TC_SAMPLE];
-      const float v = sample[((size_t)pr.x * TC_NQT + pr.y) * TC_SAMPLE + (i % TC_SAMPLE)];
+      const int2 pr = s_pairs[i / srows];
+      const float v = sample[((size_t)pr.x * TC_NQT + pr.y) * srows + (i % srows)];
       if (v < TC_INF) vals[atomicAdd(&s_fin, 1)] = (unsigned long long)f2ord(v) << 32;
     }
     __syncthreads();
     const int nfin = s_fin;
     const uint32_t kth = nfin >= k ? block_kth_key(vals, nfin, k) : 0u;
-    if (threadIdx.x == 0) tau[q] = nfin >= k ? ord2f(kth) : TC_INF;
+    if (threadIdx.x == 0) tau[q] = nfin >= k ? __fadd_rn(ord2f(kth), margin ? 2.f * tc_eps(l2 != 0, qnorm[q], max_norm, d, false) : 0.f) : TC_INF;
     return;
   }
   for (int base = 0; base < tot; base += blockDim.x) {
     sel.maybe_prune(blockDim.x);
     const int i = base + threadIdx.x;
     if (i < tot) {
-      const int2 pr = s_pairs[i / TC_SAMPLE];
-      const int s = i % TC_SAMPLE;
-      const float v = sample[((size_t)pr.x * TC_NQT + pr.y) * TC_SAMPLE + s];
+      const int2 pr = s_pairs[i / srows];
+      const int s = i % srows;
+      const float v = sample[((size_t)pr.x * TC_NQT + pr.y) * srows + s];
       if (v < TC_INF) {
         const uint32_t key = f2ord(v);
         if (sel.passes(key, i)) sel.push(key, i);
@@ -523,7 +530,8 @@ tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos,
   }
   sel.prune();
   // more sampled spans than the staging area holds: capture everything (overflow then falls back to the exact scan)
-  if (threadIdx.x == 0) tau[q] = (np_all <= TAU_PL && *sel.count >= k) ? ord2f(sel.kd[k - 1]) : TC_INF;
+  if (threadIdx.x == 0)
+    tau[q] = (np_all <= TAU_PL && *sel.count >= k) ? __fadd_rn(ord2f(sel.kd[k - 1]), margin ? 2.f * tc_eps(l2 != 0, qnorm[q], max_norm, d, false) : 0.f) : TC_INF;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1152,7 +1160,7 @@ bool tc_eligible(const IndexBase* ix, const TcView& v, int64_t nq, int k, int np
   const int64_t npairs = nq * nprobe;
   if (npairs >= (1LL << 30)) return false;
   if (tc_item_bound(v, npairs) >= (1LL << 28)) return false;
-  if (tc_sample_bound(v, npairs) * TC_NQT * TC_SAMPLE * 4 > (2LL << 30)) return false;  // sample buffer too large
+  if (tc_sample_bound(v, npairs) * TC_NQT * TC_BM * 4 > (2LL << 30)) return false;  // sample buffer too large
   return true;
 }
 
@@ -1232,7 +1240,12 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   auto& S = ix->scratch;
   ix->phase(IndexBase::PH_PLAN, s);
   TcPlan P = tc_prepare(ix, v, nq, q, probes, nprobe, s);
-  float* sample = S.alloc<float>((size_t)P.sbound * TC_NQT * TC_SAMPLE);
+  // rows sampled per span for the thresholds: 32 (one TMA box) when a query probes many local lists, the whole first
+  // tile when it probes few (a list-sharded rank sees ~nprobe / world of them): the capture count per query is
+  // ~k * rows_probed / rows_sampled, so thin samples flood the capture buffers and the finish kernel
+  static const int forced_srows = getenv("B200VS_SAMPLE_ROWS") ? atoi(getenv("B200VS_SAMPLE_ROWS")) : 0;
+  const int srows = forced_srows == TC_SAMPLE || forced_srows == TC_BM ? forced_srows : (v.owned_frac < 0.5f ? TC_BM : TC_SAMPLE);
+  float* sample = S.alloc<float>((size_t)P.sbound * TC_NQT * srows);
   float* tau = S.alloc<float>(nq);
   unsigned long long* cand = S.alloc<unsigned long long>((size_t)nq * cap);
   int* cand_cnt = S.alloc<int>(nq);
@@ -1242,7 +1255,7 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   B200VS_CUDA(cudaMemsetAsync(cand_cnt, 0, (size_t)nq * 4, s));
 
   TcParams p = tc_params(v, P, d, l2);
-  p.sample = sample; p.tau = tau; p.cand = cand; p.cand_cnt = cand_cnt; p.cap = cap;
+  p.sample = sample; p.sample_rows = srows; p.tau = tau; p.cand = cand; p.cand_cnt = cand_cnt; p.cap = cap;
   p.filt.has_range = sc.has_range; p.filt.negate = sc.negate; p.filt.rmin = sc.rmin; p.filt.rmax = sc.rmax;
   p.filt.sorted_ids = sc.sorted_ids_dev; p.filt.n_ids = sc.n_ids;
   const int pool = select_pool_cap(k, SCAN_THREADS);
@@ -1253,7 +1266,7 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   ix->phase(IndexBase::PH_SAMPLE, s);
   tc_launch(P, p, P.sbound, s);
   ix->phase(IndexBase::PH_TAU, s);
-  tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, (size_t)TAU_PL * 8 + std::max(sel_smem, (size_t)TAU_SORT * 8), s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, k, pool, tau);
+  tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, (size_t)TAU_PL * 8 + std::max(sel_smem, (size_t)TAU_SORT * 8), s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, srows, k, pool, l2 ? 1 : 0, P.qnorm, v.max_norm, d, srows == TC_BM ? 1 : 0, tau);
   // 2) capture pass: stream every probed list chunk once, keep rows under the threshold
   p.mode = 1; p.work_counter = P.work + 1;
   ix->phase(IndexBase::PH_CAPTURE, s);

@@ -55,7 +55,8 @@ struct TcParams {
   int* work_counter;        // dynamic scheduler: next work index
   const int* pair_query;    // [npairs] query index of each gathered row
   int mode;                 // 0 = sample pass, 1 = capture pass, 2 = dense pass (every score written)
-  float* sample;            // mode 0: [sample_items, TC_NQT, TC_SAMPLE]
+  float* sample;            // mode 0: [sample_items, TC_NQT, sample_rows]
+  int sample_rows;          // TC_SAMPLE (32-row box) or TC_BM (the whole first tile of each span)
   const float* tau;         // mode 1: [nq] capture threshold on the approximate score
   unsigned long long* cand; // mode 1: [nq, cap]  (ord(score) << 32 | arena row)
   int* cand_cnt;            // mode 1: [nq]
@@ -86,6 +87,7 @@ struct TcView {
   const float* vecs_lo = nullptr;  //   hi = x with the low 13 mantissa bits cleared, lo = x - hi (both exact)
   bool flat = false;         // single list covering rows [0, arena_rows)
   long long id_offset = 0;   // tc_coarse on a slice of the centroid table: added to the returned row indices
+  float owned_frac = 1.f;    // share of the lists that hold rows here (a list-sharded rank owns 1 / world of them)
   bool api_scores = false;   // tc_coarse: return the ascending ranking score (L2 distance | -ip) instead of the raw metric value
 };
 
