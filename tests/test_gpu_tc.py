@@ -119,3 +119,33 @@ def test_headline_shape_small(oracle):
     off, lx, _, lids = ix.export_lists(nlist)
     Do, Io = oracle.ivfflat_search(L2, cent, off, lx, lids, xq[:64], 10, 32, nthreads=16)
     assert_same_results(D[:64], I[:64], Do, Io)
+
+
+def test_sharded_rank_shape_dense_samples(oracle):
+    """What one rank of a list-sharded deployment holds: all centroids, rows for a quarter of the lists only.  The tile
+    path then samples the whole first tile of each span and captures under tau + 2 eps (certified by construction):
+    results stay identical to the exact scan and to the oracle, and no query needs the fallback."""
+    rng = np.random.default_rng(17)
+    n, d, nlist, own = 120_000, 256, 128, 32
+    xb = rng.random((n, d), dtype=np.float32)
+    ids = np.arange(1, n + 1, dtype=np.int64)
+    ix = b200vs.Index(IVF_FLAT, L2, d, nlist=nlist)
+    ix.train(xb[:32768])
+    cent = ix.get_trained_state()[32:].view(np.float32).reshape(nlist, d)
+    asg = oracle.assign(L2, xb, cent, nthreads=16)
+    keep = asg < own  # this "rank" owns lists [0, own)
+    for a in range(0, n, 32768):
+        m = keep[a:a + 32768]
+        if m.any():
+            ix.add(xb[a:a + 32768][m], ids[a:a + 32768][m])
+    xq = rng.random((512, d), dtype=np.float32)
+    D, I = tc_vs_exact(ix, xq, 10, nprobe=32)
+    ix.set_profiling(True)
+    ix.search(xq, 10, nprobe=32)
+    st = ix.stats()
+    ix.set_profiling(False)
+    assert st[1] == 512 and st[2] == 0, f"dense-sample thresholds must certify every query: {st}"
+    off, lx, _, lids = ix.export_lists(nlist)
+    assert off[own] == off[nlist]  # the other lists are empty here
+    Do, Io = oracle.ivfflat_search(L2, cent, off, lx, lids, xq[:64], 10, 32, nthreads=16)
+    assert_same_results(D[:64], I[:64], Do, Io)
