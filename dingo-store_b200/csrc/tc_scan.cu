@@ -1240,11 +1240,13 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   auto& S = ix->scratch;
   ix->phase(IndexBase::PH_PLAN, s);
   TcPlan P = tc_prepare(ix, v, nq, q, probes, nprobe, s);
-  // rows sampled per span for the thresholds: 32 (one TMA box) when a query probes many local lists, the whole first
-  // tile when it probes few (a list-sharded rank sees ~nprobe / world of them): the capture count per query is
-  // ~k * rows_probed / rows_sampled, so thin samples flood the capture buffers and the finish kernel
-  static const int forced_srows = getenv("B200VS_SAMPLE_ROWS") ? atoi(getenv("B200VS_SAMPLE_ROWS")) : 0;
-  const int srows = forced_srows == TC_SAMPLE || forced_srows == TC_BM ? forced_srows : (v.owned_frac < 0.5f ? TC_BM : TC_SAMPLE);
+  // rows sampled per span for the thresholds: 32 (one TMA box, capture threshold = tau) by default.
+  // B200VS_SAMPLE_ROWS=128 samples the whole first tile of each span and captures under tau + 2 eps: certified by
+  // construction (no fallback except on overflow) at the price of a longer sample / threshold pass — the setting for data
+  // whose thin samples fail certification often.  Measured on the benchmark (list-sharded over 4 GPUs as well) the thin
+  // sample wins: the finish kernel is bound by per-query latency, not by the number of captured rows.
+  const char* env_srows = getenv("B200VS_SAMPLE_ROWS");
+  const int srows = env_srows && atoi(env_srows) == TC_BM ? TC_BM : TC_SAMPLE;
   float* sample = S.alloc<float>((size_t)P.sbound * TC_NQT * srows);
   float* tau = S.alloc<float>(nq);
   unsigned long long* cand = S.alloc<unsigned long long>((size_t)nq * cap);

@@ -121,10 +121,11 @@ def test_headline_shape_small(oracle):
     assert_same_results(D[:64], I[:64], Do, Io)
 
 
-def test_sharded_rank_shape_dense_samples(oracle):
-    """What one rank of a list-sharded deployment holds: all centroids, rows for a quarter of the lists only.  The tile
-    path then samples the whole first tile of each span and captures under tau + 2 eps (certified by construction):
-    results stay identical to the exact scan and to the oracle, and no query needs the fallback."""
+def test_sharded_rank_shape_and_dense_samples(oracle):
+    """What one rank of a list-sharded deployment holds: all centroids, rows for a quarter of the lists only.  Checked
+    with the default thin threshold samples and with B200VS_SAMPLE_ROWS=128 (whole-tile samples, capture under
+    tau + 2 eps: certified by construction, so no query may need the fallback): identical to the exact scan and the oracle."""
+    import os
     rng = np.random.default_rng(17)
     n, d, nlist, own = 120_000, 256, 128, 32
     xb = rng.random((n, d), dtype=np.float32)
@@ -139,13 +140,21 @@ def test_sharded_rank_shape_dense_samples(oracle):
         if m.any():
             ix.add(xb[a:a + 32768][m], ids[a:a + 32768][m])
     xq = rng.random((512, d), dtype=np.float32)
-    D, I = tc_vs_exact(ix, xq, 10, nprobe=32)
-    ix.set_profiling(True)
-    ix.search(xq, 10, nprobe=32)
-    st = ix.stats()
-    ix.set_profiling(False)
-    assert st[1] == 512 and st[2] == 0, f"dense-sample thresholds must certify every query: {st}"
     off, lx, _, lids = ix.export_lists(nlist)
     assert off[own] == off[nlist]  # the other lists are empty here
     Do, Io = oracle.ivfflat_search(L2, cent, off, lx, lids, xq[:64], 10, 32, nthreads=16)
-    assert_same_results(D[:64], I[:64], Do, Io)
+    for srows in (None, "128"):
+        if srows:
+            os.environ["B200VS_SAMPLE_ROWS"] = srows
+        try:
+            D, I = tc_vs_exact(ix, xq, 10, nprobe=32)
+            ix.set_profiling(True)
+            ix.search(xq, 10, nprobe=32)
+            st = ix.stats()
+            ix.set_profiling(False)
+        finally:
+            os.environ.pop("B200VS_SAMPLE_ROWS", None)
+        assert st[1] == 512
+        if srows:
+            assert st[2] == 0, f"dense-sample thresholds must certify every query: {st}"
+        assert_same_results(D[:64], I[:64], Do, Io)
