@@ -51,8 +51,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exact-only", action="store_true", help="force the exact FP32 scan path")
-    ap.add_argument("--in-flight", type=int, default=2, help="batches in flight (streams / caller threads); the reference serves "
-                    "searches from a 16-thread pool, so concurrent batches are the deployed shape")
+    ap.add_argument("--in-flight", type=int, default=4, help="batches in flight (streams / caller threads); the reference serves "
+                    "searches from a 16-thread pool, so concurrent batches are the deployed shape (measured: 2 -> 1.39 M, "
+                    "3 -> 1.44 M, 4 -> 1.47 M, 8 -> 1.49 M QPS)")
     ap.add_argument("--coarse-shard", default="queries", choices=["queries", "lists"], help="multi-GPU: how the coarse quantiser is split")
     return ap.parse_args()
 
@@ -335,7 +336,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(3, args.warmup)):
+    for i in range(max(3, args.warmup, 2 * L)):  # every lane at least twice: a lane's first search sizes its scratch arena
         step_device(i)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -389,7 +390,7 @@ def main():
         for th in ths:
             th.join()
 
-    run_e2e(max(3, args.warmup))
+    run_e2e(max(3, args.warmup, 2 * L))
     barrier()
     t0 = time.perf_counter()
     run_e2e(args.steps)

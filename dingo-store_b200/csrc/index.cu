@@ -56,6 +56,11 @@ LaneGuard::LaneGuard(IndexBase* ix_, cudaStream_t s) : ix(ix_), lane(nullptr), p
     lane->last.store(stream);
     IndexBase::tl_owner = ix;
     IndexBase::tl_lane = lane;
+    if (lane->s.buf.cap == 0) {  // first search on this lane: size its arena like the largest warmed-up lane, so it does
+      size_t want = 0;            // not go through overflow blocks + consolidation (cudaFree = device-wide stalls)
+      for (auto& l : ix->lanes) want = std::max(want, l.s.buf.cap);
+      if (want) lane->s.buf.reserve(want, 0, stream);
+    }
     lane->s.reset(stream);
   } catch (...) {
     IndexBase::tl_owner = prev_owner;
