@@ -115,7 +115,6 @@ void rd(FILE* f, void* p, size_t n) { if (n && fread(p, 1, n, f) != n) fail(B200
 }  // namespace
 
 void IndexBase::save(const std::string& path) {
-  if (type == B200VS_IVF_PQ) fail(B200VS_EVECTOR_NOT_SUPPORT, "save of PQ codes is not implemented");
   const int64_t st_len = get_state(nullptr, 0);
   std::vector<unsigned char> st((size_t)std::max<int64_t>(st_len, 0));
   if (st_len > 0) get_state(st.data(), st.size());

@@ -347,7 +347,6 @@ struct IvfPqIndex : IndexBase {
     float* st = scratch.alloc<float>((size_t)n * dim);
     long long* st_ids = scratch.alloc<long long>(n);
     long long* st_list = scratch.alloc<long long>(n);
-    long long* st_slots = scratch.alloc<long long>(n);
     unsigned char* st_codes = scratch.alloc<unsigned char>((size_t)n * M);
     B200VS_CUDA(cudaMemcpyAsync(st, x, (size_t)n * dim * 4, cudaMemcpyHostToDevice, stream));
     B200VS_CUDA(cudaMemcpyAsync(st_ids, in_ids, (size_t)n * 8, cudaMemcpyHostToDevice, stream));
@@ -356,9 +355,16 @@ struct IvfPqIndex : IndexBase {
     const int wpb = 4;
     pq_encode_kernel<<<(unsigned)cdiv(n, wpb), wpb * 32, (size_t)wpb * dim * 4, stream>>>(st, st_list, centroids.p, codebooks.p, n, dim, M, st_codes);
     B200VS_CUDA(cudaGetLastError());
-    std::vector<long long> h_list(n), slots(n);
+    std::vector<long long> h_list(n);
     B200VS_CUDA(cudaMemcpyAsync(h_list.data(), st_list, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));
     B200VS_CUDA(cudaStreamSynchronize(stream));
+    append_encoded(n, st_codes, st_ids, in_ids, h_list.data());
+  }
+
+  // rows already encoded (device codes [n, M], device ids) go to the tails of their lists; callers hold the write lock
+  void append_encoded(int64_t n, const unsigned char* d_codes, const long long* d_ids, const int64_t* h_ids_in, const long long* h_list) {
+    std::vector<long long> slots(n);
+    long long* st_slots = scratch.alloc<long long>(n);
     std::vector<int> need(nlist, 0);
     for (int64_t i = 0; i < n; ++i) need[h_list[i]]++;
     L.reserve_for(need, [&](int64_t rows) {
@@ -368,9 +374,9 @@ struct IvfPqIndex : IndexBase {
       B200VS_CUDA(cudaMemcpyAsync(codes.p + (size_t)dst * M, codes.p + (size_t)src * M, (size_t)len * M, cudaMemcpyDeviceToDevice, stream));
       B200VS_CUDA(cudaMemcpyAsync(ids.p + dst, ids.p + src, (size_t)len * 8, cudaMemcpyDeviceToDevice, stream));
     });
-    for (int64_t i = 0; i < n; ++i) slots[i] = L.append((int)h_list[i], in_ids[i]);
+    for (int64_t i = 0; i < n; ++i) slots[i] = L.append((int)h_list[i], h_ids_in[i]);
     B200VS_CUDA(cudaMemcpyAsync(st_slots, slots.data(), (size_t)n * 8, cudaMemcpyHostToDevice, stream));
-    scatter_codes_kernel<<<(unsigned)cdiv(n * M, 256), 256, 0, stream>>>(st_codes, st_ids, st_slots, n, M, codes.p, ids.p);
+    scatter_codes_kernel<<<(unsigned)cdiv(n * M, 256), 256, 0, stream>>>(d_codes, d_ids, st_slots, n, M, codes.p, ids.p);
     B200VS_CUDA(cudaGetLastError());
     L.upload(stream);
     B200VS_CUDA(cudaStreamSynchronize(stream));
@@ -495,6 +501,88 @@ struct IvfPqIndex : IndexBase {
     if (mode == kFlat) return flat->memory_size();
     return (int64_t)(codes.cap + ids.cap * 8 + centroids.cap * 4 + codebooks.cap * 4 + pre.cap * 4);  // raw_ivf_pq.cc:440-450
   }
+  // Save / Load (reference: faiss::write_index / read_index of the IndexIVFPQ, vector_index_raw_ivf_pq.cc:308-377): own
+  // container "B2VSPQ01" = mode, then either the inner Flat index's rows or {trained-state blob, list offsets, ids,
+  // PQ codes in list-major order}.  Codes are restored as stored (never re-encoded: the vectors are gone).
+  void save(const std::string& path) override {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) fail(B200VS_EINTERNAL, "cannot open " + path);
+    auto wr = [&](const void* p, size_t n) { if (n && fwrite(p, 1, n, f) != n) fail(B200VS_EINTERNAL, "short write"); };
+    try {
+      int64_t hdr[8] = {0, (int64_t)mode, (int64_t)metric, dim, nlist, M, 0, 0};
+      memcpy(hdr, "B2VSPQ01", 8);
+      if (mode == kFlat) {
+        const int64_t n = flat->count();
+        std::vector<int64_t> off(2, 0), fids((size_t)n);
+        std::vector<float> vec((size_t)n * dim);
+        if (n) flat->export_lists(off.data(), vec.data(), nullptr, fids.data());
+        hdr[6] = n;
+        wr(hdr, sizeof(hdr)); wr(fids.data(), fids.size() * 8); wr(vec.data(), vec.size() * 4);
+      } else if (mode == kIvfPq) {
+        const int64_t st_len = get_state(nullptr, 0);
+        std::vector<unsigned char> st((size_t)st_len);
+        get_state(st.data(), st.size());
+        const int64_t n = count();
+        std::vector<int64_t> off((size_t)nlist + 1, 0), fids((size_t)n);
+        std::vector<uint8_t> cds((size_t)n * M);
+        export_lists(off.data(), nullptr, cds.data(), fids.data());
+        hdr[6] = n; hdr[7] = st_len;
+        wr(hdr, sizeof(hdr)); wr(st.data(), st.size()); wr(off.data(), off.size() * 8); wr(fids.data(), fids.size() * 8); wr(cds.data(), cds.size());
+      } else {
+        wr(hdr, sizeof(hdr));  // untrained: nothing but the header
+      }
+    } catch (...) { fclose(f); throw; }
+    fclose(f);
+  }
+  void load(const std::string& path) override {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) fail(B200VS_EINTERNAL, "cannot open " + path);
+    auto rd = [&](void* p, size_t n) { if (n && fread(p, 1, n, f) != n) fail(B200VS_EINTERNAL, "short read / truncated index file"); };
+    try {
+      int64_t hdr[8];
+      rd(hdr, sizeof(hdr));
+      if (memcmp(hdr, "B2VSPQ01", 8) != 0 || hdr[2] != (int64_t)metric || hdr[3] != dim || hdr[5] != M)
+        fail(B200VS_EINTERNAL, "index file does not match this index (type / metric / dimension / nsubvector)");
+      if (mode != kNone) fail(B200VS_EINTERNAL, "load into a trained index");
+      const int64_t n = hdr[6];
+      if (hdr[1] == kFlat) {
+        std::vector<int64_t> fids((size_t)n);
+        std::vector<float> vec((size_t)n * dim);
+        rd(fids.data(), fids.size() * 8); rd(vec.data(), vec.size() * 4);
+        { std::unique_lock<std::shared_mutex> wl(rw); flat.reset(make_flat(metric, dim, params)); mode = kFlat; }
+        flat->loading = true;  // rows come back exactly as stored (already normalised for cosine)
+        try {
+          for (int64_t a = 0; a < n; a += 32768) flat->add(std::min<int64_t>(32768, n - a), vec.data() + (size_t)a * dim, fids.data() + a, false);
+        } catch (...) { flat->loading = false; throw; }
+        flat->loading = false;
+      } else if (hdr[1] == kIvfPq) {
+        std::vector<unsigned char> st((size_t)hdr[7]);
+        rd(st.data(), st.size());
+        set_state(st.data(), st.size());  // centroids, codebooks, precomputed table; nlist from the blob
+        std::vector<int64_t> off((size_t)nlist + 1), fids((size_t)n);
+        std::vector<uint8_t> cds((size_t)n * M);
+        rd(off.data(), off.size() * 8); rd(fids.data(), fids.size() * 8); rd(cds.data(), cds.size());
+        if (off[nlist] != n) fail(B200VS_EINTERNAL, "corrupt index file (list offsets)");
+        std::unique_lock<std::shared_mutex> wl(rw);
+        std::lock_guard<std::mutex> gl(gpu_mu);
+        set_device();
+        quiesce();
+        std::vector<long long> h_list((size_t)n);
+        for (int l = 0; l < nlist; ++l) for (int64_t i = off[l]; i < off[l + 1]; ++i) h_list[(size_t)i] = l;
+        for (int64_t a = 0; a < n; a += 262144) {
+          const int64_t m = std::min<int64_t>(262144, n - a);
+          scratch.reset(stream);
+          unsigned char* d_codes = scratch.alloc<unsigned char>((size_t)m * M);
+          long long* d_ids = scratch.alloc<long long>(m);
+          B200VS_CUDA(cudaMemcpyAsync(d_codes, cds.data() + (size_t)a * M, (size_t)m * M, cudaMemcpyHostToDevice, stream));
+          B200VS_CUDA(cudaMemcpyAsync(d_ids, fids.data() + a, (size_t)m * 8, cudaMemcpyHostToDevice, stream));
+          append_encoded(m, d_codes, d_ids, fids.data() + a, h_list.data() + a);
+        }
+      }
+    } catch (...) { fclose(f); throw; }
+    fclose(f);
+  }
+
   void export_lists(int64_t* list_off, float* vectors, uint8_t* out_codes, int64_t* out_ids) override {
     if (mode == kFlat) { flat->export_lists(list_off, vectors, out_codes, out_ids); return; }
     std::shared_lock<std::shared_mutex> rl(rw);
