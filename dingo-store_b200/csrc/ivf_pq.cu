@@ -501,7 +501,7 @@ struct IvfPqIndex : IndexBase {
     if (mode == kFlat) return flat->memory_size();
     return (int64_t)(codes.cap + ids.cap * 8 + centroids.cap * 4 + codebooks.cap * 4 + pre.cap * 4);  // raw_ivf_pq.cc:440-450
   }
-  // Save / Load (reference: faiss::write_index / read_index of the IndexIVFPQ, vector_index_raw_ivf_pq.cc:308-377): own
+  // Save / Load (reference: faiss::write_index / read_index of the IndexIVFPQ, vector_index_raw_ivf_pq.cc:298 and :314): own
   // container "B2VSPQ01" = mode, then either the inner Flat index's rows or {trained-state blob, list offsets, ids,
   // PQ codes in list-major order}.  Codes are restored as stored (never re-encoded: the vectors are gone).
   void save(const std::string& path) override {
