@@ -175,7 +175,7 @@ def workload_config(args, world):
     return {"workload": f"IVF-Flat L2 {args.nb}x{args.dim} f32 per GPU, nlist={args.nlist} per GPU, nprobe={args.nprobe}, "
                         f"batch={args.batch} per GPU, top-{args.k} (BASELINE configs[1] at the metric's batch 1024)",
             "index": "IVF_FLAT", "metric_type": "L2", "nb_per_gpu": args.nb, "dim": args.dim, "nlist_per_gpu": args.nlist,
-            "nprobe": args.nprobe, "batch_per_gpu": args.batch, "topk": args.k, "batches_in_flight": args.in_flight,
+            "nprobe": args.nprobe, "batch_per_gpu": args.batch, "topk": args.k, "batches_in_flight": (max(1, args.in_flight) if world == 1 else 1),
             "parallelism": f"list-sharded x{world}: coarse quantiser split by {args.coarse_shard} (all_gather of the probe table), list scan of the owned lists, all_gather of per-shard top-k + merge kernel" if world > 1 else "single GPU",
             "l2_flush": "inputs larger than L2: every step streams the probed lists (~3.1 GB per GPU >> 126 MB L2)"}
 
