@@ -7,9 +7,11 @@
 //   tc_fill_pairs_kernel     gather the (TF32-rounded) queries of every list into one contiguous block
 //   tc_items_kernel          emit work items (list chunk x query group) + the list of sampled items
 //   tc_scan_kernel           *** the hot kernel: TMA -> smem ring -> tcgen05.mma (TF32) -> TMEM -> epilogue ***
-//   tc_tau_kernel            per-query capture threshold from the sampled rows
-//   tc_final_kernel          per-query window select + exact FP32 (AVX-512 order) rerank + certification
-//   tc_coarse_final_kernel   same for the dense coarse-quantiser scores
+//   tc_tau_kernel            per-query capture threshold from the sampled rows (radix select)
+//   tc_final_fast_kernel     per-query window select + exact FP32 (AVX-512 order) rerank + certification
+//                            (tc_final_kernel: the streaming variant for candidate buffers that do not fit shared memory)
+//   tc_coarse_select_kernel  coarse-quantiser finish: register-resident radix select + exact rerank of the window
+//                            (tc_coarse_final_fast_kernel / tc_coarse_final_kernel: one-sort / streaming fallbacks)
 //   tc_compact_flags_kernel  list of uncertified queries for the exact re-run
 #include <algorithm>
 #include <cmath>
@@ -199,10 +201,11 @@ static __global__ void tc_items_kernel(const int* __restrict__ cnt, const int* _
 // THE HOT KERNEL.  Persistent (one CTA per SM), warp-specialised, dynamically scheduled:
 //   warp 0 (one lane): scheduler + TMA producer — claims the next work item with one atomicAdd, publishes it through
 //                      a 4-deep smem queue, then per K block loads the A tile = 128 list rows x 32 floats (16 KB,
-//                      EVICT_FIRST: streamed once) and the B tile = 16/32/64 gathered queries x 32 floats (EVICT_LAST)
-//   warp 1 (one lane): tcgen05.mma issuer — 4 x (M=128, N=16..64, K=8) TF32 MMAs per K block into TMEM
-//   warp 2           : TMEM allocation (2 accumulator buffers x 64 columns)
-//   warps 4-7        : epilogue — tcgen05.ld the 128 x N scores, add ||x||^2, then sample / capture / dense store
+//                      EVICT_FIRST: streamed once) and the B tile = 16/32/64/128 gathered queries x 32 floats (EVICT_LAST)
+//   warp 1 (one lane): tcgen05.mma issuer — 4 x (M=128, N=16..128, K=8) TF32 MMAs per K block into TMEM
+//   warp 2           : TMEM allocation (2 accumulator buffers x 128 columns)
+//   warps 4-7        : epilogue — tcgen05.ld the 128 x N scores, add ||x||^2, then sample / capture (staged in shared
+//                      memory, flushed per item) / dense store
 // Algorithmic HBM bytes per item: rows x (d*4 + 4 + 8)  (vector, norm, id), read exactly once.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -1320,9 +1323,10 @@ bool tc_coarse_eligible(const IndexBase* ix, int64_t nq, int nrows, int nprobe) 
   return true;
 }
 
-// Error-compensated TF32 (hi*hi + lo*hi + hi*lo): three dense launches accumulate into one score matrix.  The
-// remaining error (<= 2^-19 relative) makes the exact re-score window a handful of rows even when all centroid
-// distances are nearly equal (uniform high-dimensional data).
+// Coarse quantiser: ONE dense launch of the tile kernel in split mode — error-compensated TF32, the three products
+// hi*hi + lo*hi + hi*lo accumulate into the same TMEM accumulator (the lo operands ride in the next ring stage).  The
+// operand error drops to 2^-19 relative, so the exact re-score window stays a few dozen rows even when all centroid
+// distances are nearly equal (uniform high-dimensional data); what remains of eps is the FP32 accumulation term.
 void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float* q, int nprobe, long long* out_probes,
                float* out_raw, cudaStream_t s) {
   tc_init(ix->device);

@@ -24,7 +24,7 @@ namespace b200vs {
 constexpr int TC_BM = 128;        // database rows per MMA tile (UMMA M)
 constexpr int TC_BK = 32;         // floats per K block = 128 B = one swizzle span
 constexpr int TC_NQT = 128;       // queries per work item (UMMA N <= 128): a probed list chunk is re-streamed only beyond 128 queries
-constexpr int TC_STAGES = 5;      // TMA->MMA ring depth (5 x 32 KB: leaves ~65 KB of shared memory per SM for co-resident small kernels)
+constexpr int TC_STAGES = 5;      // TMA->MMA ring depth (5 x 32 KB; + 24 KB of capture staging: ~40 KB per SM stay free for co-resident small kernels)
 constexpr int TC_THREADS = 256;   // warp0 TMA + scheduler, warp1 MMA, warp2 TMEM alloc, warps4-7 epilogue
 constexpr int TC_CHUNK = 512;     // rows per work item (list chunk): fine grain for dynamic load balance
 constexpr int TC_SPAN = 2048;     // one sampled chunk per TC_SPAN rows of a list
