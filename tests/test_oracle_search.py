@@ -192,3 +192,34 @@ def test_calc_distance_pinned_to_reference_kernels(oracle, algorithm):
     a, b = np.array([[1, 2, 3]], np.float32), np.array([[4, 6, 8]], np.float32)
     assert oracle.calc_distance(algorithm, oracle_lib.L2, a, b)[0][0, 0] == 50.0
     assert oracle.calc_distance(algorithm, oracle_lib.IP, a, b)[0][0, 0] == -39.0
+
+
+def test_hnsw_reference_hand_written_rows(oracle):
+    """The reference's hand-written HNSW fixture (test/unit_test/vector/test_vector_index_hnsw.cc:181-223): ten parallel
+    16-d rows j * m, m in {1, 3, 4, ..., 11}, ids 0..9, M = 2 links — small enough to reason about by hand."""
+    base = np.arange(16, dtype=np.float32)
+    xb = np.stack([base * m for m in (1, 3, 4, 5, 6, 7, 8, 9, 10, 11)]).astype(np.float32)
+    labels = np.arange(10, dtype=np.int64)
+    q = xb[[2, 7]]
+    # L2: a row is its own nearest neighbour at distance 0, then its neighbours in the progression
+    h = oracle_lib.OracleHnsw(oracle, L2, 16, 100, 2, 200)
+    h.add(xb, labels)
+    D, I, _, _ = h.search(q, 3, ef=10)
+    assert I[:, 0].tolist() == [2, 7] and D[:, 0].tolist() == [0.0, 0.0]
+    assert set(I[0, 1:]) == {1, 3} and set(I[1, 1:]) == {6, 8}
+    h.close()
+    # inner product (distance 1 - ip): the longest row wins for every positive query
+    h = oracle_lib.OracleHnsw(oracle, IP, 16, 100, 2, 200)
+    h.add(xb, labels)
+    D, I, _, _ = h.search(q, 2, ef=10)
+    assert I[:, 0].tolist() == [9, 9] and I[:, 1].tolist() == [8, 8]
+    assert D[0, 0] == np.float32(1.0) - np.float32(np.dot(xb[2].astype(np.float64), xb[9].astype(np.float64)))
+    h.close()
+    # cosine: every row is parallel to every other one -> every returned distance is ~0 (with M = 2 links the graph
+    # over identical normalised points need not reach all ten, so only the hits that do come back are checked)
+    h = oracle_lib.OracleHnsw(oracle, COSINE, 16, 100, 2, 200)
+    h.add(xb, labels)
+    D, I, _, _ = h.search(q, 10, ef=16)
+    hit = I >= 0
+    assert hit[:, 0].all() and len(set(I[0][hit[0]].tolist())) == int(hit[0].sum()) and np.abs(D[hit]).max() < 1e-5
+    h.close()
