@@ -475,7 +475,12 @@ def main():
         Ig, Dg = hi[0].numpy()[:sample], hd[0].numpy()[:sample]
         recall_vs_oracle = float(np.mean([len(set(a) & set(b)) / k for a, b in zip(Ig, Io)]))
         ids_exact = bool(np.array_equal(Ig, Io))
-        cpu_baseline = {"value": sample / cpu_s, "unit": "queries/s", "cores": cores, "kind": "port",
+        # the reference's own execution shape: 16 pool threads, one query per task (conf/index-gflags.conf:5, vector_index.cc:54)
+        s16 = int(min(sample, 64))
+        t = time.time()
+        o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq[:s16], k, args.nprobe, nthreads=min(16, cores))
+        qps16 = s16 / max(time.time() - t, 1e-9)
+        cpu_baseline = {"value": sample / cpu_s, "unit": "queries/s", "cores": cores, "kind": "port", "reference_shape_16_threads_qps": qps16,
                         "sample": f"first {sample} queries of the {nq}-query batch on the same trained index, {cores} threads, one query per task",
                         "recall_at_k_gpu_vs_oracle": recall_vs_oracle, "ids_bit_exact": ids_exact,
                         "max_rel_dist_err": float(np.max(np.abs(Dg - Do) / np.maximum(np.abs(Do), 1e-12)))}
