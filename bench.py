@@ -12,13 +12,16 @@ A "step" is one batched search (b200vs_search) over synthetic U[0,1) vectors.
           / its CUDA-event duration (library profiling mode, separate pass) vs MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline : the CPU oracle (restated reference path, AVX-512 order) on the box's host cores, bounded sample.
 
-Multi-GPU (torchrun, one rank per GPU): the index is sharded BY INVERTED LIST: centroids are
-replicated, every rank scans the probed lists it owns for the whole (N x 1024)-query batch, then ONE
-all_gather of the per-shard top-k over NCCL + the on-GPU k-way merge kernel.  Weak scaling: per-GPU database
-and per-GPU batch are fixed.
+Multi-GPU (torchrun, one rank per GPU): ONE logical index sharded BY INVERTED LIST through the product's
+own C ABI (b200vs_shard_*, include/b200vs.h): centroids replicated, rows routed to their list owner at add time, every
+rank scans the probed lists it owns for the whole (N x 1024)-query batch, then ONE ncclAllGather of the packed per-shard
+top-k + the on-GPU k-way merge.  torch.distributed only carries the 128-byte rendezvous blob and the timing reductions.
+Weak scaling: per-GPU database and per-GPU batch are fixed.  Every N > 1 line is verified: a query sample is answered by the
+sharded path and by the CPU oracle on every rank's exported shard (merged on rank 0) -> recall_at_10_vs_oracle, ids_bit_exact.
 
 --impl reference : times the reference's CPU implementation of the same path (the oracle port; faiss itself is
-not vendored in /root/reference) with all host threads, rank 0 only.
+not vendored in /root/reference), rank 0 only.  `value` = the reference's deployed execution shape (16 pool threads, one
+query per task: conf/index-gflags.conf:5, vector_index.cc:54); the all-host-threads number is reported beside it.
 """
 import argparse
 import ctypes
@@ -54,7 +57,7 @@ def parse():
     ap.add_argument("--in-flight", type=int, default=4, help="batches in flight (streams / caller threads); the reference serves "
                     "searches from a 16-thread pool, so concurrent batches are the deployed shape (measured: 2 -> 1.39 M, "
                     "3 -> 1.44 M, 4 -> 1.47 M, 8 -> 1.49 M QPS)")
-    ap.add_argument("--coarse-shard", default="queries", choices=["queries", "lists"], help="multi-GPU: how the coarse quantiser is split")
+    ap.add_argument("--verify", type=int, default=256, help="multi-GPU: queries answered by the sharded path AND by the CPU oracle on every rank's shard")
     return ap.parse_args()
 
 
@@ -145,26 +148,40 @@ def run_reference(args, rank, world):
     del xb
     build_s = time.time() - t0
     xq = np.random.default_rng(4321).random((args.batch, d), dtype=np.float32)
-    # calibrate a bounded sample: ~2 s of CPU work per step
+    shape_threads = min(16, cores)  # the reference's search pool: 16 workers, one query per task
+
+    def timed(nthreads, sample, steps, warmup):
+        for _ in range(warmup):
+            o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq[:sample], args.k, args.nprobe, nthreads=nthreads)
+        per = []
+        for _ in range(steps):
+            t = time.time()
+            o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq[:sample], args.k, args.nprobe, nthreads=nthreads)
+            per.append(time.time() - t)
+        return per
+
+    # calibrate a bounded sample: ~1.5 s of CPU work per step
     t = time.time()
-    o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq[: cores], args.k, args.nprobe, nthreads=cores)
-    per_q = (time.time() - t) / cores
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    sample = int(max(cores, min(args.batch, (min(2.0, budget) / max(per_q, 1e-6)))))
-    for _ in range(args.warmup):
-        o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq[:sample], args.k, args.nprobe, nthreads=cores)
-    t = time.time()
-    for _ in range(args.steps):
-        o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq[:sample], args.k, args.nprobe, nthreads=cores)
-    el = time.time() - t
+    o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq[:shape_threads * 2], args.k, args.nprobe, nthreads=shape_threads)
+    per_q = (time.time() - t) / (shape_threads * 2)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    sample = int(max(shape_threads, min(args.batch, (min(1.5, budget) / max(per_q, 1e-6)))))
+    per = timed(shape_threads, sample, args.steps, args.warmup)
+    el = float(np.sum(per))
     qps = sample * args.steps / el
+    qps_median = sample / float(np.median(per))
+    # the same sample on every host thread (a reported extra: NUMA-remote streaming makes it box-dependent)
+    per_all = timed(cores, sample, max(2, min(args.steps, 5)), 1)
+    qps_all = sample / float(np.median(per_all))
     line = {"impl": "reference", "metric": "QPS at batch-1024 top-10 dim=768; recall@10 vs ref; % HBM roofline", "value": qps,
             "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, 1),
-            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} of the {args.batch}-query batch per step, {cores} threads, one query per task; "
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": shape_threads, "kind": "port", "median_step_qps": qps_median,
+                             "all_host_threads_qps": qps_all, "host_threads": cores,
+                             "shape": "reference execution shape: 16 search-pool threads, one query per task, OpenMP 1 thread (conf/index-gflags.conf:4-5, vector_index.cc:54); value = this shape",
+                             "sample": f"{sample} of the {args.batch}-query batch per step, {shape_threads} threads, one query per task; "
                                        f"oracle port of the reference path (faiss not vendored); index built on CPU in {build_s:.0f}s "
                                        f"(kmeans niter={niter}, {max_pts} pts/centroid)"},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -175,8 +192,8 @@ def workload_config(args, world):
     return {"workload": f"IVF-Flat L2 {args.nb}x{args.dim} f32 per GPU, nlist={args.nlist} per GPU, nprobe={args.nprobe}, "
                         f"batch={args.batch} per GPU, top-{args.k} (BASELINE configs[1] at the metric's batch 1024)",
             "index": "IVF_FLAT", "metric_type": "L2", "nb_per_gpu": args.nb, "dim": args.dim, "nlist_per_gpu": args.nlist,
-            "nprobe": args.nprobe, "batch_per_gpu": args.batch, "topk": args.k, "batches_in_flight": (max(1, args.in_flight) if world == 1 else 1),
-            "parallelism": f"list-sharded x{world}: coarse quantiser split by {args.coarse_shard} (all_gather of the probe table), list scan of the owned lists, all_gather of per-shard top-k + merge kernel" if world > 1 else "single GPU",
+            "nprobe": args.nprobe, "batch_per_gpu": args.batch, "topk": args.k, "batches_in_flight": max(1, args.in_flight),
+            "parallelism": f"list-sharded x{world} behind b200vs_shard_*: coarse quantiser on the rank's query slice + all-gather of the probe table, tile scan of the owned lists, ONE ncclAllGather of packed (distance,id) top-k + merge kernel" if world > 1 else "single GPU",
             "l2_flush": "inputs larger than L2: every step streams the probed lists (~3.1 GB per GPU >> 126 MB L2)"}
 
 
@@ -204,47 +221,30 @@ def main():
     nq = args.batch * world
     t_build = time.time()
 
-    # ---- build: synthetic data, train, (multi-GPU: exchange rows to their list owners), add ----
+    # ---- build: synthetic data, train, add (multi-GPU: through the shard API, rows travel to their list owner) ----
+    L = max(1, args.in_flight)
     ix = b200vs.Index(b200vs.IVF_FLAT, b200vs.L2, d, nlist=nlist, device=local_rank)
-    chunks = [(a, x.cpu().numpy()) for a, x in gen_chunks(torch, n, d, 1234 + rank, dev)]
+    sh = None
     ntrain = min(n, nlist_local * 256)
-    train = np.concatenate([c for _, c in chunks], 0)[:ntrain] if len(chunks) > 1 else chunks[0][1][:ntrain]
     if world == 1:
+        chunks = [(a, x.cpu().numpy()) for a, x in gen_chunks(torch, n, d, 1234 + rank, dev)]
+        train = np.concatenate([c for _, c in chunks], 0)[:ntrain] if len(chunks) > 1 else chunks[0][1][:ntrain]
         ix.train(train)
         for a, x in chunks:
             for b in range(0, x.shape[0], 32768):  # kBuildVectorIndexBatchSize, src/common/constant.h:173
                 ix.add(x[b:b + 32768], np.arange(a + b + 1, a + b + 1 + min(32768, x.shape[0] - b), dtype=np.int64))
+        del chunks, train
     else:
-        # local k-means -> global centroid table (replicated); rows go to the rank that owns their list
-        loc = b200vs.Index(b200vs.IVF_FLAT, b200vs.L2, d, nlist=nlist_local, device=local_rank)
-        loc.train(train)
-        cent_local = torch.from_numpy(loc.get_trained_state()[32:].view(np.float32).reshape(nlist_local, d).copy()).to(dev)
-        loc.close()
-        cent_all = [torch.empty_like(cent_local) for _ in range(world)]
-        dist.all_gather(cent_all, cent_local)
-        cent = torch.cat(cent_all, 0).cpu().numpy()
-        ix.set_trained_state(b200vs.ivf_state_blob(cent, b200vs.L2))
-        cq = b200vs.Index(b200vs.FLAT, b200vs.L2, d, device=local_rank)  # coarse quantiser as a Flat index over centroids
-        cq.add(cent, np.arange(nlist, dtype=np.int64))
-        for a, x in chunks:
-            lst = np.concatenate([cq.search(x[b:b + 32768], 1)[1] for b in range(0, x.shape[0], 32768)], 0)
-            owner = torch.from_numpy((lst[:, 0] // nlist_local).astype(np.int64))
-            order = torch.argsort(owner, stable=True)
-            counts = torch.bincount(owner, minlength=world)
-            xs = torch.from_numpy(x)[order].to(dev)
-            gid = (torch.arange(a + 1, a + 1 + x.shape[0], dtype=torch.int64) + rank * n)[order].to(dev)
-            rc = torch.empty(world, dtype=torch.int64, device=dev)
-            dist.all_to_all_single(rc, counts.to(dev))
-            rcl, scl = rc.tolist(), counts.tolist()
-            xr = torch.empty((sum(rcl), d), dtype=torch.float32, device=dev)
-            ir = torch.empty(sum(rcl), dtype=torch.int64, device=dev)
-            dist.all_to_all_single(xr, xs, rcl, scl)
-            dist.all_to_all_single(ir, gid, rcl, scl)
-            xr, ir = xr.cpu().numpy(), ir.cpu().numpy()
-            for b in range(0, xr.shape[0], 32768):
-                ix.add(xr[b:b + 32768], ir[b:b + 32768])
-        cq.close()
-    del chunks, train
+        idb = torch.from_numpy(b200vs.Shard.unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
+        dist.broadcast(idb, 0)
+        sh = b200vs.Shard(ix, rank, world, idb.cpu().numpy(), lanes=L)
+        train = torch.cat([x for _, x in gen_chunks(torch, ntrain, d, 1234 + rank, dev)], 0).cpu().numpy()
+        sh.train(train)  # distributed: nlist / world centroids per rank, one all-gather
+        del train
+        for a, x in gen_chunks(torch, n, d, 1234 + rank, dev):
+            gid = torch.arange(a + 1, a + 1 + x.shape[0], dtype=torch.int64, device=dev) + rank * n
+            torch.cuda.synchronize()
+            sh.add_device(x.shape[0], x.data_ptr(), gid.data_ptr())
     build_s = time.time() - t_build
 
     # ---- query batches (all ranks hold the same global batch) ----
@@ -252,7 +252,6 @@ def main():
     gq.manual_seed(4321)
     nbatches = 4
     q_dev = [torch.rand((nq, d), generator=gq, device=dev, dtype=torch.float32) for _ in range(nbatches)]
-    L = max(1, args.in_flight) if world == 1 else 1  # multi-GPU: the collectives of a process group stay on one stream
     out_d = [torch.empty((nq, k), dtype=torch.float32, device=dev) for _ in range(L)]
     out_i = [torch.empty((nq, k), dtype=torch.int64, device=dev) for _ in range(L)]
     sp, _keep = b200vs.make_search_params(nprobe=args.nprobe, exact_only=args.exact_only)
@@ -260,60 +259,18 @@ def main():
     streams = [torch.cuda.Stream(device=dev) for _ in range(L)]
     torch.cuda.set_stream(main_stream)
     stream = streams[0]
-    if world > 1:
-        g_d = [torch.empty((world, nq, k), dtype=torch.float32, device=dev) for _ in range(L)]
-        g_i = [torch.empty((world, nq, k), dtype=torch.int64, device=dev) for _ in range(L)]
-        m_d = [torch.empty((nq, k), dtype=torch.float32, device=dev) for _ in range(L)]
-        m_i = [torch.empty((nq, k), dtype=torch.int64, device=dev) for _ in range(L)]
-
     launches = [0]
-
-    if world > 1:
-        # coarse quantiser of a list-sharded index.  Centroids are replicated, so the coarse work can be split either way:
-        #   queries : rank r ranks ITS slice of the batch against all centroids, one all-gather of the probe table
-        #   lists   : every rank ranks all queries against its own centroid rows, all-gather + merge of the top-nprobe
-        # Both produce the same probe table (tests/test_gpu_sharded_coarse.py); "queries" re-scores each query once.
-        np_ = args.nprobe
-        bq = args.batch
-        c_s = torch.empty((nq, np_), dtype=torch.float32, device=dev)
-        c_l = torch.empty((nq, np_), dtype=torch.int64, device=dev)
-        p_l = torch.empty((nq, np_), dtype=torch.int64, device=dev)
-        if args.coarse_shard == "lists":
-            gc_s = torch.empty((world, nq, np_), dtype=torch.float32, device=dev)
-            gc_l = torch.empty((world, nq, np_), dtype=torch.int64, device=dev)
-            p_s = torch.empty((nq, np_), dtype=torch.float32, device=dev)
-
-    def sharded_search(q_ptr, ln, st):
-        """list-sharded batch: coarse (sharded) -> all-gather -> local list scan -> all-gather -> merged top-k"""
-        if args.coarse_shard == "queries":
-            ix.coarse_device(bq, q_ptr + rank * bq * d * 4, np_, 0, nlist, c_s.data_ptr(), c_l.data_ptr(), stream=st.cuda_stream)
-            launches[0] += ix.stats()[0]
-            with torch.cuda.stream(st):
-                dist.all_gather_into_tensor(p_l.view(-1), c_l[:bq].view(-1))
-        else:
-            ix.coarse_device(nq, q_ptr, np_, rank * nlist_local, (rank + 1) * nlist_local, c_s.data_ptr(), c_l.data_ptr(), stream=st.cuda_stream)
-            launches[0] += ix.stats()[0]
-            with torch.cuda.stream(st):
-                dist.all_gather_into_tensor(gc_s.view(-1), c_s.view(-1))
-                dist.all_gather_into_tensor(gc_l.view(-1), c_l.view(-1))
-            b200vs.merge_topk_device(local_rank, world, nq, np_, gc_s.data_ptr(), gc_l.data_ptr(), p_s.data_ptr(), p_l.data_ptr(), st.cuda_stream)
-            launches[0] += 1
-        ix.search_probes_device(nq, q_ptr, k, p_l.data_ptr(), np_, out_d[ln].data_ptr(), out_i[ln].data_ptr(), stream=st.cuda_stream, sp=sp)
-        launches[0] += ix.stats()[0]
-        with torch.cuda.stream(st):
-            dist.all_gather_into_tensor(g_d[ln].view(-1), out_d[ln].view(-1))
-            dist.all_gather_into_tensor(g_i[ln].view(-1), out_i[ln].view(-1))
-        b200vs.merge_topk_device(local_rank, world, nq, k, g_d[ln].data_ptr(), g_i[ln].data_ptr(), m_d[ln].data_ptr(), m_i[ln].data_ptr(), st.cuda_stream)
-        launches[0] += 1
+    seq = [0]  # batch sequence number of the sharded path: the same on every rank, so batch i uses the same communicator everywhere
 
     def step_device(i, lanes=L):
         ln = i % lanes
         st = streams[ln]
         q = q_dev[i % nbatches]
         if world > 1:
-            sharded_search(q.data_ptr(), ln, st)
-            return
-        ix.search_device(nq, q.data_ptr(), k, out_d[ln].data_ptr(), out_i[ln].data_ptr(), stream=st.cuda_stream, sp=sp)
+            sh.search_device(nq, q.data_ptr(), k, out_d[ln].data_ptr(), out_i[ln].data_ptr(), stream=st.cuda_stream, sp=sp, seq=seq[0])
+            seq[0] += 1
+        else:
+            ix.search_device(nq, q.data_ptr(), k, out_d[ln].data_ptr(), out_i[ln].data_ptr(), stream=st.cuda_stream, sp=sp)
         launches[0] += ix.stats()[0]
 
     def timed_device(steps, lanes):
@@ -361,29 +318,24 @@ def main():
     hd = [torch.empty((nq, k), dtype=torch.float32).pin_memory() for _ in range(L)]
     hi = [torch.empty((nq, k), dtype=torch.int64).pin_memory() for _ in range(L)]
 
-    def step_e2e(i, ln=0):
+    def step_e2e(i, ln=0, base=0):
         q = q_host[i % nbatches]
         if world == 1:
             ix.search_raw(nq, q.data_ptr(), k, hd[ln].data_ptr(), hi[ln].data_ptr(), sp=sp)  # H2D + search + D2H, synchronous
-            return float(hd[ln][0, 0])
-        st = streams[ln]
-        with torch.cuda.stream(st):
-            qd = q.to(dev, non_blocking=True)
-        sharded_search(qd.data_ptr(), ln, st)
-        with torch.cuda.stream(st):
-            hd[ln].copy_(m_d[ln], non_blocking=True)
-            hi[ln].copy_(m_i[ln], non_blocking=True)
-        st.synchronize()
+        else:  # H2D of the rank's slice + NVLink all-gather of the batch + sharded search + D2H, synchronous
+            sh.search_raw(nq, q.data_ptr(), k, hd[ln].data_ptr(), hi[ln].data_ptr(), sp=sp, seq=base + i)
         return float(hd[ln][0, 0])
 
     def run_e2e(steps):
-        if world > 1 or L == 1:  # collectives stay on one caller thread
+        base = seq[0]
+        seq[0] += steps
+        if L == 1:
             for i in range(steps):
-                step_e2e(i, 0)
+                step_e2e(i, 0, base)
             return
-        def worker(t):
+        def worker(t):  # one caller thread per batch in flight; explicit sequence numbers keep the ranks' collectives aligned
             for i in range(t, steps, L):
-                step_e2e(i, t)
+                step_e2e(i, t, base)
         ths = [threading.Thread(target=worker, args=(t,)) for t in range(L)]
         for th in ths:
             th.start()
@@ -414,27 +366,16 @@ def main():
     phase_ms = {}
     for i in range(3):
         if world > 1:
-            sharded_search(q_dev[i % nbatches].data_ptr(), 0, stream)
-            torch.cuda.synchronize()
-            phase_ms = ix.phase_times()  # of the probe-driven list scan; the coarse call is timed below
+            sh.search_device(nq, q_dev[i % nbatches].data_ptr(), k, out_d[0].data_ptr(), out_i[0].data_ptr(), stream=stream.cuda_stream, sp=sp, seq=seq[0])
+            seq[0] += 1
         else:
             ix.search_device(nq, q_dev[i % nbatches].data_ptr(), k, out_d[0].data_ptr(), out_i[0].data_ptr(), stream=stream.cuda_stream, sp=sp)
         torch.cuda.synchronize()
         st = ix.stats()
         kt.append(st[3] / 1e9)
         rows = st[4]
-        if world == 1:
-            phase_ms = ix.phase_times()
+        phase_ms = ix.phase_times()
     prof_stats = list(st)
-    if world > 1:  # coarse call alone
-        if args.coarse_shard == "queries":
-            ix.coarse_device(bq, q_dev[0].data_ptr() + rank * bq * d * 4, np_, 0, nlist, c_s.data_ptr(), c_l.data_ptr(), stream=stream.cuda_stream)
-        else:
-            ix.coarse_device(nq, q_dev[0].data_ptr(), np_, rank * nlist_local, (rank + 1) * nlist_local, c_s.data_ptr(), c_l.data_ptr(), stream=stream.cuda_stream)
-        torch.cuda.synchronize()
-        cp = ix.phase_times()
-        for kk in ("coarse_prep", "coarse_scan", "coarse_final"):
-            phase_ms[kk] = cp[kk]
     ix.set_profiling(False)
     peak, how = measured_peaks()
     kern_s = float(np.mean(kt)) if kt and min(kt) > 0 else None
@@ -485,6 +426,39 @@ def main():
                         "recall_at_k_gpu_vs_oracle": recall_vs_oracle, "ids_bit_exact": ids_exact,
                         "max_rel_dist_err": float(np.max(np.abs(Dg - Do) / np.maximum(np.abs(Do), 1e-12)))}
 
+    # ---- N > 1: answer a query sample through the sharded product path AND with the CPU oracle on every rank's shard ----
+    verify = None
+    if world > 1 and args.verify > 0:
+        import oracle_lib
+        import b200vs.shard as shard_host
+        o = oracle_lib.load()
+        ns = int(min(args.verify, nq))
+        xq = q_host[0].numpy()[:ns].copy()
+        Dg, Ig = sh.search(xq, k, seq=seq[0], nprobe=args.nprobe)  # host-pointer collective call, merged result on every rank
+        seq[0] += 1
+        off, lx, _, lids = ix.export_lists(nlist)  # this rank's rows; lists owned elsewhere are empty
+        cent = ix.get_trained_state()[32:].view(np.float32).reshape(nlist, d)
+        threads = max(1, (os.cpu_count() or 1) // world)
+        t = time.time()
+        Do, Io = o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xq, k, args.nprobe, nthreads=threads)
+        oracle_s = time.time() - t
+        gd = [torch.empty((ns, k), dtype=torch.float32, device=dev) for _ in range(world)]
+        gi = [torch.empty((ns, k), dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(gd, torch.from_numpy(Do).to(dev))
+        dist.all_gather(gi, torch.from_numpy(Io).to(dev))
+        cnt = torch.tensor([ix.get_count()], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt)
+        if rank == 0:
+            Dm, Im = shard_host.merge_topk(torch.stack(gd).cpu().numpy(), torch.stack(gi).cpu().numpy(), k)  # MergeSearchResults rule
+            verify = {"queries": ns, "ids_bit_exact": bool(np.array_equal(Ig, Im)),
+                      "dist_bit_exact": bool(np.array_equal(Dg.view(np.uint32), Dm.view(np.uint32))),
+                      "recall_at_k_gpu_vs_oracle": float(np.mean([len(set(a) & set(b)) / k for a, b in zip(Ig, Im)])),
+                      "max_rel_dist_err": float(np.max(np.abs(Dg - Dm) / np.maximum(np.abs(Dm), 1e-12))),
+                      "rows_in_index_all_ranks": int(cnt.item()), "oracle_seconds_per_rank": oracle_s,
+                      "how": f"first {ns} queries of the batch: b200vs_shard_search on {world} ranks vs the CPU oracle run on every rank's exported shard "
+                             f"(global centroids, {threads} threads per rank), per-rank top-k merged on rank 0 with the MergeSearchResults rule"}
+            recall_vs_oracle = verify["recall_at_k_gpu_vs_oracle"]
+
     if rank == 0:
         line = {"metric": "QPS at batch-1024 top-10 dim=768; recall@10 vs ref; % HBM roofline", "value": qps, "unit": "queries/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
@@ -495,10 +469,11 @@ def main():
                 "single_stream": {"value": nq * args.steps / (ms_single / 1e3), "unit": "queries/s", "ms_per_step": ms_single / args.steps,
                                   "note": "same K steps strictly back to back on one stream"},
                 "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "recall_at_10_vs_oracle": recall_vs_oracle, "build_seconds": build_s, "search_stats": ix.stats(), "profile_stats": prof_stats, "phase_ms": {a: round(v, 4) for a, v in phase_ms.items()}}
+                "recall_at_10_vs_oracle": recall_vs_oracle, "sharded_verification": verify, "build_seconds": build_s, "search_stats": ix.stats(), "profile_stats": prof_stats, "phase_ms": {a: round(v, 4) for a, v in phase_ms.items()}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        sh.close()
         dist.destroy_process_group()
 
 

@@ -11,10 +11,6 @@
 
 using namespace b200vs;
 
-struct b200vs_index {
-  IndexBase* impl;
-};
-
 namespace {
 
 template <class F>
@@ -39,10 +35,7 @@ int guarded(F&& f) {
   }
 }
 
-IndexBase* get(b200vs_index* h) {
-  if (!h || !h->impl) fail(B200VS_EILLEGAL_PARAMETERS, "null index handle");
-  return h->impl;
-}
+IndexBase* get(b200vs_index* h) { return index_impl(h); }
 
 // resolve search params; uploads the sorted id list into scratch (stream-ordered)
 SearchCtx make_ctx(IndexBase* ix, const b200vs_search_params* sp, cudaStream_t s) {
@@ -134,6 +127,38 @@ int b200vs_add_with_ids(b200vs_index* h, int64_t n, const float* x, const int64_
     IndexBase* ix = get(h);
     if (n <= 0 || !x || !ids) fail(B200VS_EILLEGAL_PARAMETERS, "vector_with_ids is empty");  // flat.cc:123-125
     ix->add(n, x, ids, upsert != 0);
+    return B200VS_OK;
+  });
+}
+
+int b200vs_add_with_ids_device(b200vs_index* h, int64_t n, const float* x_dev, const int64_t* ids_dev, const int64_t* lists_dev, int upsert) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    if (n <= 0 || !x_dev || !ids_dev) fail(B200VS_EILLEGAL_PARAMETERS, "vector_with_ids is empty");
+    ix->add_dev(n, x_dev, (const long long*)ids_dev, (const long long*)lists_dev, upsert != 0, false);
+    return B200VS_OK;
+  });
+}
+
+int b200vs_assign_device(b200vs_index* h, int64_t n, const float* x_dev, int64_t* out_lists_dev) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    if (n <= 0 || !x_dev || !out_lists_dev) fail(B200VS_EILLEGAL_PARAMETERS, "bad assign arguments");
+    std::shared_lock<std::shared_mutex> rl(ix->rw);
+    ix->set_device();
+    LaneGuard lane(ix, nullptr);
+    const float* q = ix->prepare_queries(n, x_dev, lane.stream);
+    ix->assign_lists_dev(n, q, (long long*)out_lists_dev, lane.stream);
+    B200VS_CUDA(cudaStreamSynchronize(lane.stream));
+    return B200VS_OK;
+  });
+}
+
+int b200vs_reserve_lists(b200vs_index* h, const int64_t* rows_per_list, int32_t nlist) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    if (!rows_per_list || nlist <= 0) fail(B200VS_EILLEGAL_PARAMETERS, "bad reserve arguments");
+    ix->reserve_lists(rows_per_list, nlist);
     return B200VS_OK;
   });
 }

@@ -465,16 +465,14 @@ struct IvfFlatIndex : IndexBase {
     return (int64_t)need;
   }
 
-  // assign rows (device, already normalised) to their nearest centroid: IndexFlat quantiser, k = 1
+  // assign rows (device, already normalised) to their nearest centroid: IndexFlat quantiser, k = 1.  Large batches go
+  // through the tensor-core coarse pass (certified exact, so the labels equal the exact scan's).
   void assign_dev(const float* x_dev, int64_t n, long long* out_list_dev, cudaStream_t s) {
-    ScanJob j;
-    j.l2 = metric == B200VS_L2;
-    j.vecs = centroids.p; j.ids = cent_ids.p; j.d = dim; j.mode = 0; j.n = nlist;
-    const int64_t chunk = 32768;
+    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(32768, (1LL << 28) / std::max(1, nlist)));
     for (int64_t a = 0; a < n; a += chunk) {
       const int64_t m = std::min(chunk, n - a);
-      const size_t mark = scratch.mark();
-      run_scan(this, j, m, x_dev + (size_t)a * dim, 1, nullptr, nullptr, out_list_dev + a, nullptr, s);
+      const auto mark = scratch.mark();
+      coarse(m, x_dev + (size_t)a * dim, 1, s, true, out_list_dev + a);
       scratch.release(mark);  // stream-ordered reuse
     }
   }
@@ -484,6 +482,21 @@ struct IvfFlatIndex : IndexBase {
   void train(int64_t n, const float* x) override;
 
   void add(int64_t n, const float* x, const int64_t* in_ids, bool upsert) override;
+  void add_dev(int64_t n, const float* x_dev, const long long* ids_dev, const long long* lists_dev, bool upsert, bool prepared) override;
+  void add_locked(int64_t n, float* st, const long long* st_ids, const int64_t* h_ids_in, const long long* lists_dev, bool upsert, bool prepared);
+  void reserve_lists(const int64_t* rows_per_list, int n_lists) override;
+  int nlist_now() const override { return nlist; }
+  void assign_lists_dev(int64_t n, const float* x_dev, long long* out_lists_dev, cudaStream_t s) override {
+    if (!trained) fail(B200VS_EVECTOR_NOT_TRAIN, "not train");
+    assign_dev(x_dev, n, out_lists_dev, s);
+  }
+  void coarse_probes_dev(int64_t nq, const float* q_prepared, int nprobe, long long* out_lists, cudaStream_t s) override {
+    if (!trained) fail(B200VS_EVECTOR_NOT_TRAIN, "not train");
+    coarse(nq, q_prepared, nprobe, s, true, out_lists);
+  }
+  void search_probes_prepared_dev(int64_t nq, const float* q, int k, const long long* probes, int nprobe, const SearchCtx& sc, float* od,
+                                  long long* oi, cudaStream_t s) override;
+  int resolve_nprobe_api(const SearchCtx& sc) const override { return resolve_nprobe(sc); }
   int64_t remove(int64_t n, const int64_t* del) override;
   int64_t remove_locked(int64_t n, const int64_t* del);
   void maybe_compact();
@@ -500,16 +513,15 @@ struct IvfFlatIndex : IndexBase {
   void search_probes_dev(int64_t nq, const float* xq, int k, const long long* probes, int nprobe, const SearchCtx& sc, float* od,
                          long long* oi, cudaStream_t s) override;
 
-  long long* coarse(int64_t nq, const float* q, int nprobe, cudaStream_t s, bool allow_tc = true) {
+  long long* coarse(int64_t nq, const float* q, int nprobe, cudaStream_t s, bool allow_tc = true, long long* out = nullptr) {
+    long long* probes = out ? out : scratch.alloc<long long>((size_t)nq * nprobe);
     if (allow_tc && tc_coarse_eligible(this, nq, nlist, nprobe)) {  // dense TF32 scores + certified exact re-score
-      long long* probes = scratch.alloc<long long>((size_t)nq * nprobe);
       tc_coarse(this, cent_view(), metric == B200VS_L2, nq, q, nprobe, probes, nullptr, s);
       return probes;
     }
     ScanJob j;
     j.l2 = metric == B200VS_L2;
     j.vecs = centroids.p; j.ids = cent_ids.p; j.d = dim; j.mode = 0; j.n = nlist;
-    long long* probes = scratch.alloc<long long>((size_t)nq * nprobe);
     run_scan(this, j, nq, q, nprobe, nullptr, nullptr, probes, nullptr, s);
     return probes;
   }
@@ -542,18 +554,38 @@ void IvfFlatIndex::train(int64_t n, const float* x) {
   if (n < k) k = 1;  // "data size too small, nlist degenerate to 1", ivf_flat.cc:676-680
   std::vector<float> cent;
   kmeans_gpu(this, metric, dim, n, x, k, 10, 256, 1234, cent, [&](const float* xd, int64_t m, const float* cd, int kk, long long* out) {
-    // assignment against the CURRENT centroids cd (device)
+    // assignment against the CURRENT centroids cd (device): tensor-core coarse pass when the shapes allow (certified
+    // exact labels), else the exact scan
+    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(32768, (1LL << 28) / std::max(1, kk)));
+    const auto mark0 = scratch.mark();
+    TcView cv;
+    const bool use_tc = tc_coarse_eligible(this, std::min(chunk, m), kk, 1);
+    if (use_tc) {
+      float* hi = scratch.alloc<float>((size_t)kk * dim);
+      float* lo = scratch.alloc<float>((size_t)kk * dim);
+      float* nr = scratch.alloc<float>(kk);
+      launch_split_rows(cd, kk, dim, hi, lo, stream);
+      launch_row_norms(cd, kk, dim, nr, stream);
+      cv.vecs = cd; cv.ids = cent_ids.p; cv.norms = nr; cv.arena_rows = kk; cv.list_off = d_coff.p; cv.list_len = nullptr;
+      cv.nlist = 1; cv.flat = true; cv.total_chunks = (kk + TC_CHUNK - 1) / TC_CHUNK; cv.max_chunks_per_list = (int)cv.total_chunks;
+      cv.max_norm = device_max_norm(this, nr, kk, stream); cv.vecs_hi = hi; cv.vecs_lo = lo;
+    }
     ScanJob j;
     j.l2 = metric == B200VS_L2;
     j.vecs = cd; j.ids = cent_ids.p; j.d = dim; j.mode = 0; j.n = kk;
-    const int64_t chunk = 32768;
     for (int64_t a = 0; a < m; a += chunk) {
       const int64_t mm = std::min(chunk, m - a);
-      const size_t mark = scratch.mark();
-      run_scan(this, j, mm, xd + (size_t)a * dim, 1, nullptr, nullptr, out + a, nullptr, stream);
+      const auto mark = scratch.mark();
+      if (use_tc && mm >= 16) tc_coarse(this, cv, metric == B200VS_L2, mm, xd + (size_t)a * dim, 1, out + a, nullptr, stream);
+      else run_scan(this, j, mm, xd + (size_t)a * dim, 1, nullptr, nullptr, out + a, nullptr, stream);
       scratch.release(mark);
     }
-  }, [&](int kk) { cent_ids.free(); cent_ids.reserve(kk, 0, stream); launch_iota(cent_ids.p, kk, stream); });
+    scratch.release(mark0);
+  }, [&](int kk) {
+    cent_ids.free(); cent_ids.reserve(kk, 0, stream); launch_iota(cent_ids.p, kk, stream);
+    d_coff.reserve(1, 0, stream);
+    B200VS_CUDA(cudaMemsetAsync(d_coff.p, 0, 8, stream));
+  });
   install_centroids(cent.data(), k);
 }
 
@@ -564,21 +596,57 @@ void IvfFlatIndex::add(int64_t n, const float* x, const int64_t* in_ids, bool up
   set_device();
   quiesce();
   scratch.reset(stream);
-  if (upsert) remove_locked(n, in_ids);  // ivf_flat.cc:115-118
   float* st = scratch.alloc<float>((size_t)n * dim);
   long long* st_ids = scratch.alloc<long long>(n);
-  long long* st_list = scratch.alloc<long long>(n);
-  long long* st_slots = scratch.alloc<long long>(n);
   B200VS_CUDA(cudaMemcpyAsync(st, x, (size_t)n * dim * 4, cudaMemcpyHostToDevice, stream));
   B200VS_CUDA(cudaMemcpyAsync(st_ids, in_ids, (size_t)n * 8, cudaMemcpyHostToDevice, stream));
-  if (metric == B200VS_COSINE && !loading) launch_normalize_faiss(st, n, dim, stream);
-  assign_dev(st, n, st_list, stream);
+  add_locked(n, st, st_ids, in_ids, nullptr, upsert, loading);
+}
+
+void IvfFlatIndex::add_dev(int64_t n, const float* x_dev, const long long* ids_dev, const long long* lists_dev, bool upsert, bool prepared) {
+  std::unique_lock<std::shared_mutex> wl(rw);
+  if (!trained) fail(B200VS_EVECTOR_NOT_TRAIN, "not train");
+  std::lock_guard<std::mutex> gl(gpu_mu);
+  set_device();
+  quiesce();
+  scratch.reset(stream);
+  float* st = const_cast<float*>(x_dev);
+  if (metric == B200VS_COSINE && !prepared) {  // the normaliser works in place: keep the caller's rows intact
+    st = scratch.alloc<float>((size_t)n * dim);
+    B200VS_CUDA(cudaMemcpyAsync(st, x_dev, (size_t)n * dim * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  add_locked(n, st, ids_dev, nullptr, lists_dev, upsert, prepared);
+}
+
+// rw + gpu_mu held, scratch reset.  st / st_ids: device rows and ids (st may be normalised in place); h_ids_in: host copy
+// of the ids when the caller has one; lists_dev: precomputed lists or NULL.
+void IvfFlatIndex::add_locked(int64_t n, float* st, const long long* st_ids, const int64_t* h_ids_in, const long long* lists_dev, bool upsert,
+                              bool prepared) {
+  std::vector<int64_t> h_ids_buf;
+  if (!h_ids_in) {
+    h_ids_buf.resize(n);
+    B200VS_CUDA(cudaMemcpyAsync(h_ids_buf.data(), st_ids, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));
+    B200VS_CUDA(cudaStreamSynchronize(stream));
+    h_ids_in = h_ids_buf.data();
+  }
+  if (upsert) remove_locked(n, h_ids_in);  // ivf_flat.cc:115-118
+  long long* st_slots = scratch.alloc<long long>(n);
+  if (metric == B200VS_COSINE && !prepared) launch_normalize_faiss(st, n, dim, stream);
+  const long long* st_list = lists_dev;
+  if (!st_list) {
+    long long* tmp = scratch.alloc<long long>(n);
+    assign_dev(st, n, tmp, stream);
+    st_list = tmp;
+  }
   std::vector<long long> h_list(n), slots(n);
   B200VS_CUDA(cudaMemcpyAsync(h_list.data(), st_list, (size_t)n * 8, cudaMemcpyDeviceToHost, stream));
   B200VS_CUDA(cudaStreamSynchronize(stream));
   // host: reserve slots (may relocate lists / grow the arena)
   std::vector<int> need(nlist, 0);
-  for (int64_t i = 0; i < n; ++i) need[h_list[i]]++;
+  for (int64_t i = 0; i < n; ++i) {
+    if (h_list[i] < 0 || h_list[i] >= nlist) fail(B200VS_EILLEGAL_PARAMETERS, "list id out of range");
+    need[h_list[i]]++;
+  }
   L.reserve_for(need, [&](int64_t arena_rows) {
     vecs.reserve((size_t)arena_rows * dim, (size_t)L.arena_used_before * dim, stream);
     ids.reserve((size_t)arena_rows, (size_t)L.arena_used_before, stream);
@@ -588,13 +656,43 @@ void IvfFlatIndex::add(int64_t n, const float* x, const int64_t* in_ids, bool up
     B200VS_CUDA(cudaMemcpyAsync(ids.p + dst, ids.p + src, (size_t)len * 8, cudaMemcpyDeviceToDevice, stream));
     B200VS_CUDA(cudaMemcpyAsync(norms.p + dst, norms.p + src, (size_t)len * 4, cudaMemcpyDeviceToDevice, stream));
   });
-  for (int64_t i = 0; i < n; ++i) slots[i] = L.append((int)h_list[i], in_ids[i]);
+  for (int64_t i = 0; i < n; ++i) slots[i] = L.append((int)h_list[i], h_ids_in[i]);
   B200VS_CUDA(cudaMemcpyAsync(st_slots, slots.data(), (size_t)n * 8, cudaMemcpyHostToDevice, stream));
   float* st_norms = scratch.alloc<float>(n);
   launch_scatter_rows(st, st_ids, st_slots, n, dim, vecs.p, ids.p, norms.p, st_norms, stream);
   max_norm = std::max(max_norm, device_max_norm(this, st_norms, n, stream));
   L.upload(stream);
   B200VS_CUDA(cudaStreamSynchronize(stream));
+}
+
+// one arena allocation holding every list at its final size (+ 1/16 slack): bulk builds of large shards
+void IvfFlatIndex::reserve_lists(const int64_t* rows_per_list, int n_lists) {
+  std::unique_lock<std::shared_mutex> wl(rw);
+  if (!trained) fail(B200VS_EVECTOR_NOT_TRAIN, "not train");
+  if (n_lists != nlist) fail(B200VS_EILLEGAL_PARAMETERS, "reserve_lists: list count does not match the trained index");
+  std::lock_guard<std::mutex> gl(gpu_mu);
+  set_device();
+  quiesce();
+  if (L.live + L.dead > 0) fail(B200VS_EILLEGAL_PARAMETERS, "reserve_lists needs an empty index");
+  int64_t used = 0;
+  for (int l = 0; l < nlist; ++l) {
+    const int64_t want = rows_per_list[l];
+    if (want < 0 || want >= (1LL << 31) - 64) fail(B200VS_EILLEGAL_PARAMETERS, "reserve_lists: bad list size");
+    ListMeta& m = L.lists[l];
+    m.off = used; m.len = 0; m.dead = 0;
+    m.cap = want ? IvfLists::round32(want + want / 16 + 32) : 0;
+    used += m.cap;
+  }
+  const int64_t tail = std::max<int64_t>(used / 64, 4096);  // room for lists that still outgrow their reservation
+  L.arena_used = L.arena_used_before = used;
+  L.arena_cap = used + tail;
+  vecs.free(); ids.free(); norms.free();
+  vecs.reserve((size_t)L.arena_cap * dim, 0, stream);
+  ids.reserve((size_t)L.arena_cap, 0, stream);
+  norms.reserve((size_t)L.arena_cap, 0, stream);
+  B200VS_CUDA(cudaMemsetAsync(ids.p, 0xFF, (size_t)L.arena_cap * 8, stream));  // id -1 = unused slot
+  L.h_ids.assign(L.arena_cap, -1);
+  L.upload(stream);
 }
 
 int64_t IvfFlatIndex::remove_locked(int64_t n, const int64_t* del) {
@@ -691,7 +789,12 @@ void IvfFlatIndex::coarse_range_dev(int64_t nq, const float* xq, int nprobe, int
 void IvfFlatIndex::search_probes_dev(int64_t nq, const float* xq, int k, const long long* probes, int nprobe, const SearchCtx& sc, float* od,
                                      long long* oi, cudaStream_t s) {
   if (!trained) { fill_empty_results(nq, k, od, oi, s); return; }
-  const float* q = prepare_queries(nq, xq, s);
+  search_probes_prepared_dev(nq, prepare_queries(nq, xq, s), k, probes, nprobe, sc, od, oi, s);
+}
+
+void IvfFlatIndex::search_probes_prepared_dev(int64_t nq, const float* q, int k, const long long* probes, int nprobe, const SearchCtx& sc,
+                                              float* od, long long* oi, cudaStream_t s) {
+  if (!trained) { fill_empty_results(nq, k, od, oi, s); return; }
   if (profiling) profile_probed(this, probes, nq * nprobe, nlist, L.d_len.p, s);
   const TcView v = view();
   if (L.live > 0 && tc_eligible(this, v, nq, k, nprobe, sc)) {

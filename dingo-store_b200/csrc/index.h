@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdint>
 #include <cstring>
@@ -53,15 +54,17 @@ struct Scratch {
   DevBuf<unsigned char> buf;
   size_t used = 0;
   std::vector<std::pair<void*, size_t>> overflow;  // extra cudaMalloc blocks when buf is too small
+  size_t peak_overflow = 0;                        // most overflow bytes alive at once since the last reset
   ~Scratch() { release_overflow(); }
   void release_overflow() { for (auto& o : overflow) cudaFree(o.first); overflow.clear(); }
+  size_t overflow_bytes() const { size_t b = 0; for (auto& o : overflow) b += o.second + 256; return b; }
   void reset(cudaStream_t s) {
-    if (!overflow.empty()) {  // grow the main buffer so the next search fits without overflow blocks
-      size_t extra = 0;
-      for (auto& o : overflow) extra += o.second + 256;
+    peak_overflow = std::max(peak_overflow, overflow_bytes());
+    if (peak_overflow) {  // grow the main buffer so the next search fits without overflow blocks
       B200VS_CUDA(cudaStreamSynchronize(s));
       release_overflow();
-      size_t want = (buf.cap + extra) * 3 / 2;
+      size_t want = (buf.cap + peak_overflow) * 3 / 2;
+      peak_overflow = 0;
       buf.free();
       buf.reserve(want, 0, s);
     }
@@ -75,6 +78,16 @@ struct Scratch {
     B200VS_CUDA(cudaMalloc(&p, bytes));
     overflow.emplace_back(p, bytes);
     return reinterpret_cast<T*>(p);
+  }
+  // scoped reuse inside one operation (chunk loops): everything allocated after mark() is handed back by release().
+  // Overflow blocks taken in between are freed (cudaFree waits for the device), so a loop over many chunks holds one
+  // chunk's worth of memory, not the sum.
+  struct Mark { size_t used, nover; };
+  Mark mark() const { return Mark{used, overflow.size()}; }
+  void release(const Mark& m) {
+    peak_overflow = std::max(peak_overflow, overflow_bytes());
+    while (overflow.size() > m.nover) { cudaFree(overflow.back().first); overflow.pop_back(); }
+    used = m.used;
   }
 };
 
@@ -128,8 +141,8 @@ struct IndexBase {
     IndexBase* ix;
     template <class T> T* alloc(size_t n) { return ix->cur().s.alloc<T>(n); }
     void reset(cudaStream_t st) { ix->cur().s.reset(st); }
-    size_t mark() { return ix->cur().s.used; }
-    void release(size_t m) { ix->cur().s.used = m; }
+    Scratch::Mark mark() { return ix->cur().s.mark(); }
+    void release(const Scratch::Mark& m) { ix->cur().s.release(m); }
   } scratch{this};
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // profiling only (one caller at a time): CUDA-event marks between the phases of a search, b200vs_last_phase_times
@@ -191,6 +204,38 @@ struct IndexBase {
     (void)nq; (void)xq; (void)k; (void)probes; (void)nprobe; (void)sc; (void)od; (void)oi; (void)s;
     fail(B200VS_EVECTOR_NOT_SUPPORT, "probe-driven search only exists for IVF_FLAT");
   }
+  // ---- device-pointer write path and the building blocks of a list-sharded deployment (shard.cu); IVF_FLAT only ----
+  // rows / ids already on this device.  lists_dev (nullable) = the inverted list of every row, decided by the caller;
+  // prepared = store the rows exactly as given (cosine rows are already normalised).
+  virtual void add_dev(int64_t n, const float* x_dev, const long long* ids_dev, const long long* lists_dev, bool upsert, bool prepared) {
+    (void)n; (void)x_dev; (void)ids_dev; (void)lists_dev; (void)upsert; (void)prepared;
+    fail(B200VS_EVECTOR_NOT_SUPPORT, "device-pointer add only exists for IVF_FLAT");
+  }
+  // nearest-centroid assignment of prepared rows (faiss quantizer->assign): out_lists_dev[n], on stream s (a lane must be held)
+  virtual void assign_lists_dev(int64_t n, const float* x_dev, long long* out_lists_dev, cudaStream_t s) {
+    (void)n; (void)x_dev; (void)out_lists_dev; (void)s;
+    fail(B200VS_EVECTOR_NOT_SUPPORT, "list assignment only exists for IVF_FLAT");
+  }
+  // pre-size every inverted list (rows_per_list[nlist]) in ONE arena allocation: bulk builds of large shards never
+  // relocate a list or re-allocate the arena (a 77 GB shard cannot afford a 2x peak)
+  virtual void reserve_lists(const int64_t* rows_per_list, int nlist) {
+    (void)rows_per_list; (void)nlist;
+    fail(B200VS_EVECTOR_NOT_SUPPORT, "list reservation only exists for IVF_FLAT");
+  }
+  virtual int nlist_now() const { return 1; }
+  // probe table (set semantics, order unspecified) of prepared queries into a caller buffer
+  virtual void coarse_probes_dev(int64_t nq, const float* q_prepared, int nprobe, long long* out_lists, cudaStream_t s) {
+    (void)nq; (void)q_prepared; (void)nprobe; (void)out_lists; (void)s;
+    fail(B200VS_EVECTOR_NOT_SUPPORT, "coarse quantiser only exists for IVF_FLAT");
+  }
+  // search_probes_dev on queries that are already prepared (normalised for cosine)
+  virtual void search_probes_prepared_dev(int64_t nq, const float* q_prepared, int k, const long long* probes, int nprobe, const SearchCtx& sc,
+                                          float* od, long long* oi, cudaStream_t s) {
+    (void)nq; (void)q_prepared; (void)k; (void)probes; (void)nprobe; (void)sc; (void)od; (void)oi; (void)s;
+    fail(B200VS_EVECTOR_NOT_SUPPORT, "probe-driven search only exists for IVF_FLAT");
+  }
+  virtual int resolve_nprobe_api(const SearchCtx& sc) const { (void)sc; return 1; }
+
   virtual int64_t count() const = 0;
   virtual int64_t deleted_count() const { return 0; }
   virtual int64_t memory_size() const = 0;
@@ -213,6 +258,16 @@ struct LaneGuard {
   LaneGuard(IndexBase* ix_, cudaStream_t s);
   ~LaneGuard();
 };
+
+}  // namespace b200vs
+struct b200vs_index {  // the opaque handle of include/b200vs.h
+  b200vs::IndexBase* impl;
+};
+namespace b200vs {
+inline IndexBase* index_impl(b200vs_index* h) {
+  if (!h || !h->impl) fail(B200VS_EILLEGAL_PARAMETERS, "null index handle");
+  return h->impl;
+}
 
 IndexBase* make_flat(b200vs_metric m, int d, const b200vs_params& p);
 IndexBase* make_ivf_flat(b200vs_metric m, int d, const b200vs_params& p);

@@ -264,7 +264,7 @@ struct IvfPqIndex : IndexBase {
     const int64_t chunk = 32768;
     for (int64_t a = 0; a < n; a += chunk) {
       const int64_t m = std::min(chunk, n - a);
-      const size_t mark = scratch.mark();
+      const auto mark = scratch.mark();
       run_scan(this, j, m, x_dev + (size_t)a * dd, 1, nullptr, nullptr, out + a, nullptr, stream);
       scratch.release(mark);
     }

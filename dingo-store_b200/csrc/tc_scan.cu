@@ -16,10 +16,12 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
 
 #include "scan_kernels.cuh"
 #include "sm100_ptx.cuh"
 #include "tc_scan.cuh"
+#include "warp_select.cuh"
 
 namespace b200vs {
 
@@ -475,10 +477,11 @@ static __global__ void __launch_bounds__(SCAN_THREADS)
 tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos, const int* __restrict__ cnt,
               const int* __restrict__ item_off, const int* __restrict__ list_len, const TcItem* __restrict__ items, int nprobe,
               const float* __restrict__ sample, int srows, int k, int pool_cap, int l2, const float* __restrict__ qnorm,
-              float max_norm, int d, int margin, float* tau) {
+              float max_norm, int d, int margin, float* tau, const int* redo) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_np;
   const int q = blockIdx.x;
+  if (redo && !redo[q]) return;  // only the queries the warp kernel could not finish
   int2* s_pairs = reinterpret_cast<int2*>(smem);  // [TAU_PL]
   if (threadIdx.x == 0) s_np = 0;
   BlockSelect sel;
@@ -535,6 +538,78 @@ tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos,
   // more sampled spans than the staging area holds: capture everything (overflow then falls back to the exact scan)
   if (threadIdx.x == 0)
     tau[q] = (np_all <= TAU_PL && *sel.count >= k) ? __fadd_rn(ord2f(sel.kd[k - 1]), margin ? 2.f * tc_eps(l2 != 0, qnorm[q], max_norm, d, false) : 0.f) : TC_INF;
+}
+
+
+// Warp-per-query form of the threshold kernel (the common case: <= WT_PAIRS sampled spans of TC_SAMPLE rows per query).
+// Lanes walk the probe list, stage one (sample slot, column) per sampled span, then the warp reads one span per step
+// (32 contiguous floats) and radix-selects the k-th smallest finite score.  Queries with more spans set redo[q] and are
+// finished by tc_tau_kernel.
+constexpr int WT_WARPS = 4;
+constexpr int WT_PAIRS = 64;
+static __global__ void __launch_bounds__(WT_WARPS * 32)
+tc_tau_warp_kernel(const long long* __restrict__ probes, const int* __restrict__ pos, const int* __restrict__ cnt,
+                   const int* __restrict__ item_off, const int* __restrict__ list_len, const TcItem* __restrict__ items, int nprobe,
+                   const float* __restrict__ sample, int k, int nq, float* tau, int* redo) {
+  __shared__ int s_hist[WT_WARPS][WS_BINS];
+  __shared__ int s_pair[WT_WARPS][WT_PAIRS];
+  __shared__ uint32_t s_val[WT_WARPS][WT_PAIRS * TC_SAMPLE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * WT_WARPS + warp;
+  if (q >= nq) return;
+  int np = 0;
+  for (int base = 0; base < nprobe; base += 32) {
+    const int j = base + lane;
+    int nspan = 0, first = 0, ng = 1, g = 0, n = 0;
+    if (j < nprobe) {
+      const long long l = probes[(size_t)q * nprobe + j];
+      const int len = l >= 0 ? list_len[l] : 0;
+      if (len > 0) {
+        ng = (cnt[l] + TC_NQT - 1) / TC_NQT;
+        const int ps = pos[(size_t)q * nprobe + j];
+        g = ps / TC_NQT; n = ps % TC_NQT;
+        nspan = (len + TC_SPAN - 1) / TC_SPAN;
+        first = item_off[l];
+      }
+    }
+    int incl = nspan;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const int off = np + incl - nspan;
+    for (int sp = 0; sp < nspan; ++sp)
+      if (off + sp < WT_PAIRS) s_pair[warp][off + sp] = items[first + sp * (TC_SPAN / TC_CHUNK) * ng + g].sample_slot * TC_NQT + n;
+    np += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (np > WT_PAIRS) { if (lane == 0) redo[q] = 1; return; }
+  if (lane == 0) redo[q] = 0;
+  __syncwarp();
+  // one lane per sampled span: its 32 scores are one 128-byte line, fetched as 8 independent 16-byte loads, so the whole
+  // query's sample is in flight at once (a warp-per-span loop would serialise one L2 round trip per span)
+  __shared__ int s_nfin[WT_WARPS];
+  if (lane == 0) s_nfin[warp] = 0;
+  __syncwarp();
+  for (int p = lane; p < np; p += 32) {
+    const float4* src = reinterpret_cast<const float4*>(sample + (size_t)s_pair[warp][p] * TC_SAMPLE);
+    float4 v[TC_SAMPLE / 4];
+#pragma unroll
+    for (int j = 0; j < TC_SAMPLE / 4; ++j) v[j] = src[j];
+    const float* f = reinterpret_cast<const float*>(v);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < TC_SAMPLE; ++j) c += f[j] < TC_INF ? 1 : 0;
+    int o = atomicAdd(&s_nfin[warp], c);
+#pragma unroll
+    for (int j = 0; j < TC_SAMPLE; ++j) if (f[j] < TC_INF) s_val[warp][o++] = f2ord(f[j]);
+  }
+  __syncwarp();
+  const int nfin = s_nfin[warp];
+  float t = TC_INF;
+  if (nfin >= k) {
+    int c_le;
+    const uint32_t* vals = s_val[warp];
+    t = ord2f(warp_kth_key(k, s_hist[warp], [&](auto f) { for (int i = lane; i < nfin; i += 32) f(vals[i]); }, c_le));
+  }
+  if (lane == 0) tau[q] = t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -683,10 +758,11 @@ static __global__ void __launch_bounds__(SCAN_THREADS)
 tc_final_fast_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int cap,
                      const float* __restrict__ tau, const float* __restrict__ qnorm, float max_norm, const float* __restrict__ q,
                      const float* __restrict__ vecs, const long long* __restrict__ ids, int d, int k, float* out_dist,
-                     long long* out_ids, int* flags) {
+                     long long* out_ids, int* flags, const int* redo) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_m;
   const int qi = blockIdx.x;
+  if (redo && !redo[qi]) return;  // only the queries the warp kernel could not finish
   float* qs = reinterpret_cast<float*>(smem);
   const size_t qbytes = ((size_t)d * 4 + 15) / 16 * 16;
   long long* ex_id = reinterpret_cast<long long*>(smem + qbytes);                    // [FIN_MAXW]
@@ -717,6 +793,126 @@ tc_final_fast_kernel(const unsigned long long* __restrict__ cand, const int* __r
     out_ids[(size_t)qi * k + i] = id;
   }
   if (threadIdx.x == 0) flags[qi] = certified ? 0 : 1;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Finish kernel for the common case (at most HF_MAXW rows inside the 2*eps window): one 128-thread CTA per query.  Same
+// rule as tc_final_fast_kernel — k-th approximate score A_k, every captured row with score <= A_k + 2 eps re-scored
+// exactly in the reference order, exact top-k by (distance, id), certification — but the selection is done by ONE warp
+// with shuffles / ballots and a warp-private histogram (no block-wide radix passes), all 32 quads of the CTA then
+// re-score the window rows together (the ~40 random 3 KB row gathers per query are what this kernel waits on, so they are
+// all issued at once) and a rank sort orders the exact pairs: three block barriers in total, 16 CTAs per SM.
+// Queries whose window is larger set redo[q] = 1 and are finished by the block kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int HF_THREADS = 128;
+constexpr int HF_STAGE = 512;   // captured keys staged in shared memory (the rest is re-read from global / L2 in every pass)
+constexpr int HF_MAXW = 256;
+constexpr int HF_ROW_BYTES = 24 * 1024;  // dynamic shared memory for the staged window rows (+ the query row)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// The ~40 window rows of a query are random 3 KB gathers from HBM: what the kernel waits on.  They are staged into
+// shared memory with 16-byte cp.async copies (no registers held, so a CTA keeps a whole group of rows in flight), then
+// quads re-score them from shared memory in the reference order.  rows_g rows of `pitch` bytes per group (d % 4 == 0).
+template <bool L2>
+static __global__ void __launch_bounds__(HF_THREADS)
+tc_final_hybrid_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int cap,
+                       const float* __restrict__ tau, const float* __restrict__ qnorm, float max_norm, const float* __restrict__ q,
+                       const float* __restrict__ vecs, const long long* __restrict__ ids, int d, int k, int rows_g, int pitch,
+                       float* out_dist, long long* out_ids, int* flags, int* redo) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];  // [pitch] query row, then rows_g staged rows
+  __shared__ int s_hist[WS_BINS];
+  __shared__ unsigned long long s_keys[HF_STAGE];
+  __shared__ int s_rows[HF_MAXW];
+  __shared__ uint32_t s_kd[HF_MAXW];
+  __shared__ long long s_id[HF_MAXW];
+  __shared__ int s_m;
+  __shared__ float s_ak;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x;
+  const int total = cand_cnt[qi];
+  const int n = min(total, cap);
+  const unsigned long long* c = cand + (size_t)qi * cap;
+  const int nst = min(n, HF_STAGE);
+  const int cpr = d >> 2;  // 16-byte chunks per row
+  for (int i = threadIdx.x; i < cpr; i += HF_THREADS) cp_async16(s_dyn + (size_t)i * 16, q + (size_t)qi * d + i * 4);
+  for (int i = threadIdx.x; i < nst; i += HF_THREADS) s_keys[i] = c[i];
+  const float two_eps = 2.f * tc_eps(L2, qnorm[qi], max_norm, d, false);
+  __syncthreads();
+  if (warp == 0) {
+    auto key_at = [&](int i) -> unsigned long long { return i < nst ? s_keys[i] : c[i]; };
+    float a_k = TC_INF;
+    if (n >= k) {
+      int c_le;
+      a_k = ord2f(warp_kth_key(k, s_hist, [&](auto f) { for (int i = lane; i < n; i += 32) f((uint32_t)(key_at(i) >> 32)); }, c_le));
+    }
+    const float window = a_k + two_eps;
+    int m = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      unsigned long long e = 0;
+      bool in = false;
+      if (i < n) { e = key_at(i); in = ord2f((uint32_t)(e >> 32)) <= window; }
+      const unsigned msk = __ballot_sync(0xffffffffu, in);
+      const int p = m + __popc(msk & ((1u << lane) - 1u));
+      if (in && p < HF_MAXW) s_rows[p] = (int)(uint32_t)(e & 0xffffffffull);
+      m += __popc(msk);
+    }
+    if (lane == 0) { s_m = m; s_ak = a_k; }
+  }
+  __syncthreads();
+  const int m = s_m;
+  if (m > HF_MAXW) { if (threadIdx.x == 0) redo[qi] = 1; return; }
+  const int quad = threadIdx.x >> 2, t = threadIdx.x & 3;
+  const float* qs = reinterpret_cast<const float*>(s_dyn);
+  unsigned char* stage = s_dyn + pitch;
+  for (int g0 = 0; g0 < m; g0 += rows_g) {
+    const int ng = min(rows_g, m - g0);
+    for (int i = threadIdx.x; i < ng * cpr; i += HF_THREADS) {
+      const int r = i / cpr, ch = i - r * cpr;
+      cp_async16(stage + (size_t)r * pitch + (size_t)ch * 16, vecs + (size_t)(uint32_t)s_rows[g0 + r] * d + ch * 4);
+    }
+    if (threadIdx.x < ng) s_id[g0 + threadIdx.x] = ids[(uint32_t)s_rows[g0 + threadIdx.x]];
+    cp_async_wait_all();
+    __syncthreads();
+    for (int base = 0; base < ng; base += HF_THREADS / 4) {
+      const int i = base + quad;
+      const bool valid = i < ng;
+      const float v = quad_distance<L2>(reinterpret_cast<const float*>(stage + (size_t)(valid ? i : 0) * pitch), qs, d, t, true);
+      if (valid && t == 0) s_kd[g0 + i] = f2ord(L2 ? v : -v);
+    }
+    __syncthreads();
+  }
+  const int have = min(m, k);
+  for (int e = threadIdx.x; e < m; e += HF_THREADS) {
+    const uint32_t d0 = s_kd[e];
+    const long long i0 = s_id[e];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const uint32_t dj = s_kd[j];
+      const long long ij = s_id[j];
+      rank += (key_less(dj, ij, d0, i0) || (dj == d0 && ij == i0 && j < e)) ? 1 : 0;
+    }
+    if (rank < k) {
+      const float v = ord2f(d0);
+      const float raw = L2 ? v : -v;
+      out_dist[(size_t)qi * k + rank] = L2 ? raw : __fsub_rn(1.0f, raw);
+      out_ids[(size_t)qi * k + rank] = i0;
+    }
+  }
+  for (int i = have + threadIdx.x; i < k; i += HF_THREADS) { out_dist[(size_t)qi * k + i] = 0.f; out_ids[(size_t)qi * k + i] = -1; }
+  if (threadIdx.x == 0) {
+    const float tq = tau[qi];
+    const float a_k = s_ak;
+    flags[qi] = ((total <= cap) && (tq == TC_INF || a_k + two_eps <= tq)) ? 0 : 1;
+    redo[qi] = 0;
+  }
 }
 
 template <bool L2>
@@ -839,13 +1035,14 @@ template <bool L2, int KPT>
 static __global__ void __launch_bounds__(SEL_THREADS)
 tc_coarse_select_kernel(const float* __restrict__ dense, long long ld, int nrows, const float* __restrict__ qnorm, float max_norm,
                         const float* __restrict__ q, const float* __restrict__ vecs, int d, int k, long long id_offset, int api_scores,
-                        long long* out_probes, float* out_raw, int* flags) {
+                        long long* out_probes, float* out_raw, int* flags, const int* redo_in) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ SelShared S;
   __shared__ int s_rows[SEL_WCAP];
   __shared__ uint32_t s_kd[SEL_WCAP];
   __shared__ long long s_id[SEL_WCAP];
   const int qi = blockIdx.x;
+  if (redo_in && !redo_in[qi]) { if (threadIdx.x == 0) flags[qi] = 0; return; }  // finished by the warp kernel
   float* qs = reinterpret_cast<float*>(smem);
   for (int i = threadIdx.x; i < d; i += SEL_THREADS) qs[i] = q[(size_t)qi * d + i];
   uint32_t key[KPT];
@@ -902,15 +1099,106 @@ tc_coarse_select_kernel(const float* __restrict__ dense, long long ld, int nrows
   }
 }
 
+
+// Coarse finish for small centroid tables (nrows <= 32 * KPT <= 1024): one 128-thread CTA per query.  Warp 0 holds the
+// score row in registers and does the selection (same full / set modes and +-2 eps rule as tc_coarse_select_kernel) with
+// shuffles / ballots; all 32 quads then re-score the window rows together; a rank sort orders them.  Three block
+// barriers.  Queries whose re-score window exceeds HC_MAXW rows set flags[qi] = 1 and go to the block kernels.
+constexpr int HC_THREADS = 128;
+constexpr int HC_MAXW = 256;
+template <bool L2, int KPT>
+static __global__ void __launch_bounds__(HC_THREADS)
+tc_coarse_select_hybrid_kernel(const float* __restrict__ dense, long long ld, int nrows, const float* __restrict__ qnorm, float max_norm,
+                               const float* __restrict__ q, const float* __restrict__ vecs, int d, int k, long long id_offset, int api_scores,
+                               long long* out_probes, float* out_raw, int* flags) {
+  __shared__ int s_hist[WS_BINS];
+  __shared__ int s_rows[HC_MAXW];
+  __shared__ uint32_t s_kd[HC_MAXW];
+  __shared__ long long s_id[HC_MAXW];
+  __shared__ int s_m, s_ns;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x;
+  if (warp == 0) {
+    uint32_t key[KPT];
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+      const int r = lane + j * 32;
+      key[j] = r < nrows ? f2ord(dense[(size_t)qi * ld + r]) : 0xFFFFFFFFu;
+    }
+    int c_le;
+    const uint32_t kth = warp_kth_key(k, s_hist, [&](auto f) {
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) if (key[j] != 0xFFFFFFFFu) f(key[j]);
+    }, c_le);
+    const float a_k = ord2f(kth);
+    const float two_eps = 2.f * tc_eps(L2, qnorm[qi], max_norm, d, true);
+    const uint32_t thr_hi = f2ord(__fadd_ru(a_k, two_eps));
+    const uint32_t thr_lo = f2ord(__fsub_rd(a_k, two_eps));
+    const bool set_mode = out_raw == nullptr && c_le == k;
+    int ns = 0, m = 0;
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+      const int r = lane + j * 32;
+      const bool in = key[j] <= thr_hi && key[j] != 0xFFFFFFFFu;
+      const bool sure = in && set_mode && key[j] <= thr_lo;
+      const unsigned ms = __ballot_sync(0xffffffffu, sure), mw = __ballot_sync(0xffffffffu, in && !sure);
+      const unsigned lt = (1u << lane) - 1u;
+      if (sure) out_probes[(size_t)qi * k + ns + __popc(ms & lt)] = r + id_offset;
+      if (in && !sure) { const int p = m + __popc(mw & lt); if (p < HC_MAXW) s_rows[p] = r; }
+      ns += __popc(ms);
+      m += __popc(mw);
+    }
+    if (lane == 0) { s_m = m; s_ns = ns; }
+  }
+  __syncthreads();
+  const int m = s_m, ns = s_ns;
+  if (m > HC_MAXW) { if (threadIdx.x == 0) flags[qi] = 1; return; }  // (the block kernel rewrites the whole output row)
+  const int quad = threadIdx.x >> 2, t = threadIdx.x & 3;
+  const bool vec = (d & 3) == 0;
+  const float* qrow = q + (size_t)qi * d;
+  for (int base = 0; base < m; base += HC_THREADS / 4) {
+    const int i = base + quad;
+    const bool valid = i < m;
+    const long long row = (long long)s_rows[valid ? i : 0];
+    const float v = quad_distance<L2>(vecs + (size_t)row * d, qrow, d, t, vec);
+    if (valid && t == 0) { s_kd[i] = f2ord(L2 ? v : -v); s_id[i] = row; }
+  }
+  __syncthreads();
+  const int need = k - ns;  // slots still open (set mode), all k otherwise
+  for (int e = threadIdx.x; e < m; e += HC_THREADS) {
+    const uint32_t d0 = s_kd[e];
+    const long long i0 = s_id[e];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const uint32_t dj = s_kd[j];
+      const long long ij = s_id[j];
+      rank += (key_less(dj, ij, d0, i0) || (dj == d0 && ij == i0 && j < e)) ? 1 : 0;
+    }
+    if (rank < need) {
+      out_probes[(size_t)qi * k + ns + rank] = i0 + id_offset;
+      if (out_raw) {
+        const float v = ord2f(d0);
+        out_raw[(size_t)qi * k + rank] = api_scores ? v : (L2 ? v : -v);
+      }
+    }
+  }
+  for (int i = m + threadIdx.x; i < need; i += HC_THREADS) {
+    out_probes[(size_t)qi * k + ns + i] = -1;
+    if (out_raw) out_raw[(size_t)qi * k + i] = 0.f;
+  }
+  if (threadIdx.x == 0) flags[qi] = 0;
+}
+
 template <bool L2>
 static __global__ void __launch_bounds__(SCAN_THREADS)
 tc_final_kernel(const unsigned long long* __restrict__ cand, const int* __restrict__ cand_cnt, int cap,
                 const float* __restrict__ tau, const float* __restrict__ qnorm, float max_norm, const float* __restrict__ q,
                 const float* __restrict__ vecs, const long long* __restrict__ ids, int d, int k, int pool_cap,
-                float* out_dist, long long* out_ids, int* flags) {
+                float* out_dist, long long* out_ids, int* flags, const int* redo) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_m;
   const int qi = blockIdx.x;
+  if (redo && !redo[qi]) return;
   float* qs = reinterpret_cast<float*>(smem);
   const size_t qbytes = ((size_t)d * 4 + 15) / 16 * 16;
   int* s_rows = reinterpret_cast<int*>(smem + qbytes);  // [FIN_SEG]
@@ -1136,9 +1424,16 @@ static int64_t tc_sample_bound(const TcView& v, int64_t npairs) {  // spans are 
 }
 static int tc_cand_cap(int k) { return std::min(16384, std::max(2048, next_pow2(128 * k))); }
 
-static int g_num_sms = 0;
-static void tc_init(int device) {
-  if (g_num_sms) return;
+// Per-device one-time setup: cudaFuncSetAttribute applies to the CURRENT device only, and one process may hold indexes
+// on several GPUs (b200vs_params.device), so the opt-in shared-memory limits are raised once per device ordinal.
+constexpr int TC_MAX_DEVICES = 64;
+constexpr int TC_FAST_SMEM = 200 * 1024;  // opt-in limit of the one-sort finish kernels
+static std::mutex g_tc_init_mu;
+static int g_dev_sms[TC_MAX_DEVICES] = {0};
+static int tc_init(int device) {
+  if (device < 0 || device >= TC_MAX_DEVICES) fail(B200VS_EILLEGAL_PARAMETERS, "bad CUDA device ordinal");
+  std::lock_guard<std::mutex> g(g_tc_init_mu);
+  if (g_dev_sms[device]) return g_dev_sms[device];
   int sms = 0;
   B200VS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   B200VS_CUDA(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
@@ -1147,11 +1442,14 @@ static void tc_init(int device) {
   B200VS_CUDA(cudaFuncSetAttribute(tc_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));  // + static smem
   B200VS_CUDA(cudaFuncSetAttribute(tc_coarse_final_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));  // + static smem
   B200VS_CUDA(cudaFuncSetAttribute(tc_coarse_final_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));  // + static smem
-  B200VS_CUDA(cudaFuncSetAttribute(tc_final_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  B200VS_CUDA(cudaFuncSetAttribute(tc_final_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  B200VS_CUDA(cudaFuncSetAttribute(tc_coarse_final_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  B200VS_CUDA(cudaFuncSetAttribute(tc_coarse_final_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  g_num_sms = sms;  // only after every attribute call succeeded
+  B200VS_CUDA(cudaFuncSetAttribute(tc_final_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_FAST_SMEM));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_final_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_FAST_SMEM));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_coarse_final_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_FAST_SMEM));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_coarse_final_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_FAST_SMEM));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_final_hybrid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  B200VS_CUDA(cudaFuncSetAttribute(tc_final_hybrid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  g_dev_sms[device] = sms;  // only after every attribute call succeeded
+  return sms;
 }
 
 bool tc_eligible(const IndexBase* ix, const TcView& v, int64_t nq, int k, int nprobe, const SearchCtx& sc) {
@@ -1163,7 +1461,7 @@ bool tc_eligible(const IndexBase* ix, const TcView& v, int64_t nq, int k, int np
   const int64_t npairs = nq * nprobe;
   if (npairs >= (1LL << 30)) return false;
   if (tc_item_bound(v, npairs) >= (1LL << 28)) return false;
-  if (tc_sample_bound(v, npairs) * TC_NQT * TC_BM * 4 > (2LL << 30)) return false;  // sample buffer too large
+  if (tc_sample_bound(v, npairs) * TC_NQT * TC_SAMPLE * 4 > (4LL << 30)) return false;  // sample buffer too large (TC_SAMPLE rows per sampled item)
   return true;
 }
 
@@ -1176,13 +1474,15 @@ struct TcPlan {
   int64_t bound, sbound, npairs;
   CUtensorMap tmA, tmA32, tmB16, tmB32, tmB64, tmB128, tmQ;
   bool gather;
+  int num_sms;
 };
 
 static TcPlan tc_prepare(IndexBase* ix, const TcView& v, int64_t nq, const float* q, const long long* probes, int nprobe, cudaStream_t s) {
-  tc_init(ix->device);
+  const int num_sms = tc_init(ix->device);
   const int d = ix->dim;
   auto& S = ix->scratch;
   TcPlan P;
+  P.num_sms = num_sms;
   P.npairs = nq * nprobe;
   P.bound = tc_item_bound(v, P.npairs);
   P.sbound = tc_sample_bound(v, P.npairs);
@@ -1228,7 +1528,7 @@ static TcParams tc_params(const TcView& v, const TcPlan& P, int d, bool l2) {
 }
 
 static void tc_launch(const TcPlan& P, const TcParams& p, int64_t work_bound, cudaStream_t s) {
-  const int grid = (int)std::min<int64_t>(g_num_sms, std::max<int64_t>(1, work_bound));
+  const int grid = (int)std::min<int64_t>(P.num_sms, std::max<int64_t>(1, work_bound));
   tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(P.tmA, P.tmA32, P.tmB16, P.tmB32, P.tmB64, P.tmB128, P.tmA, P.tmB16, P.tmB32, P.tmB64, P.tmB128, P.tmQ, p);
   B200VS_CUDA(cudaGetLastError());
 }
@@ -1249,7 +1549,7 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   // whose thin samples fail certification often.  Measured on the benchmark (list-sharded over 4 GPUs as well) the thin
   // sample wins: the finish kernel is bound by per-query latency, not by the number of captured rows.
   const char* env_srows = getenv("B200VS_SAMPLE_ROWS");
-  const int srows = env_srows && atoi(env_srows) == TC_BM ? TC_BM : TC_SAMPLE;
+  const int srows = env_srows && atoi(env_srows) == TC_BM && P.sbound * TC_NQT * TC_BM * 4 <= (4LL << 30) ? TC_BM : TC_SAMPLE;
   float* sample = S.alloc<float>((size_t)P.sbound * TC_NQT * srows);
   float* tau = S.alloc<float>(nq);
   unsigned long long* cand = S.alloc<unsigned long long>((size_t)nq * cap);
@@ -1271,7 +1571,14 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   ix->phase(IndexBase::PH_SAMPLE, s);
   tc_launch(P, p, P.sbound, s);
   ix->phase(IndexBase::PH_TAU, s);
-  tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, (size_t)TAU_PL * 8 + std::max(sel_smem, (size_t)TAU_SORT * 8), s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, srows, k, pool, l2 ? 1 : 0, P.qnorm, v.max_norm, d, srows == TC_BM ? 1 : 0, tau);
+  int* redo = S.alloc<int>(nq);
+  const size_t tau_smem = (size_t)TAU_PL * 8 + std::max(sel_smem, (size_t)TAU_SORT * 8);
+  if (srows == TC_SAMPLE) {  // warp per query; the block kernel only redoes queries with more sampled spans than a warp stages
+    tc_tau_warp_kernel<<<(unsigned)cdiv(nq, WT_WARPS), WT_WARPS * 32, 0, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, k, (int)nq, tau, redo);
+    tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, tau_smem, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, srows, k, pool, l2 ? 1 : 0, P.qnorm, v.max_norm, d, 0, tau, redo);
+  } else {
+    tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, tau_smem, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, srows, k, pool, l2 ? 1 : 0, P.qnorm, v.max_norm, d, 1, tau, nullptr);
+  }
   // 2) capture pass: stream every probed list chunk once, keep rows under the threshold
   p.mode = 1; p.work_counter = P.work + 1;
   ix->phase(IndexBase::PH_CAPTURE, s);
@@ -1283,13 +1590,23 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   // 3) window select + exact rerank + certification
   ix->phase(IndexBase::PH_FINAL, s);
   const size_t fast_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_MAXW * 16 + (size_t)cap * 8;
-  if (fast_smem <= 200 * 1024) {  // one 64-bit sort of the captured rows + a small exact sort
-    if (l2) tc_final_fast_kernel<true><<<(unsigned)nq, SCAN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
-    else tc_final_fast_kernel<false><<<(unsigned)nq, SCAN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags);
+  const int* fin_redo = nullptr;
+  const int hf_pitch = d * 4 + 16;  // staged row pitch: 16-byte aligned, rows land on different banks
+  const int hf_rows = std::min(32, std::max(HF_ROW_BYTES, 2 * hf_pitch) / hf_pitch - 1);
+  const size_t hsm = (size_t)(hf_rows + 1) * hf_pitch;
+  if (2 * k <= HF_MAXW && hf_rows >= 1 && hsm <= 96 * 1024) {  // warp select + block re-score; the block kernels below only redo queries whose window exceeds HF_MAXW rows
+    if (l2) tc_final_hybrid_kernel<true><<<(unsigned)nq, HF_THREADS, hsm, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, hf_rows, hf_pitch, out_dist, out_ids, flags, redo);
+    else tc_final_hybrid_kernel<false><<<(unsigned)nq, HF_THREADS, hsm, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, hf_rows, hf_pitch, out_dist, out_ids, flags, redo);
+    fin_redo = redo;
+    ix->launch_count(1);
+  }
+  if (fast_smem <= (size_t)TC_FAST_SMEM) {  // one 64-bit sort of the captured rows + a small exact sort
+    if (l2) tc_final_fast_kernel<true><<<(unsigned)nq, SCAN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags, fin_redo);
+    else tc_final_fast_kernel<false><<<(unsigned)nq, SCAN_THREADS, fast_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, out_dist, out_ids, flags, fin_redo);
   } else {
     const size_t fin_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + sel_smem;
-    if (l2) tc_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags);
-    else tc_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags);
+    if (l2) tc_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags, fin_redo);
+    else tc_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, fin_smem, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, pool, out_dist, out_ids, flags, fin_redo);
   }
   tc_compact_flags_kernel<<<1, 1024, 0, s>>>(flags, (int)nq, qmap, qcount);
   B200VS_CUDA(cudaGetLastError());
@@ -1319,6 +1636,7 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
 bool tc_coarse_eligible(const IndexBase* ix, int64_t nq, int nrows, int nprobe) {
   if (ix->dim % 4 != 0 || ix->dim < 32) return false;
   if (nq < 16 || nrows < 64 || nprobe > 1024) return false;
+  if (ix->dim > 8192) return false;  // the finish kernels keep the query row in (un-opted) dynamic shared memory
   if ((int64_t)nq * nrows * 4 > (1LL << 30)) return false;  // dense score matrix
   return true;
 }
@@ -1329,7 +1647,7 @@ bool tc_coarse_eligible(const IndexBase* ix, int64_t nq, int nrows, int nprobe) 
 // distances are nearly equal (uniform high-dimensional data); what remains of eps is the FP32 accumulation term.
 void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float* q, int nprobe, long long* out_probes,
                float* out_raw, cudaStream_t s) {
-  tc_init(ix->device);
+  const int num_sms = tc_init(ix->device);
   const int d = ix->dim;
   const int nrows = (int)v.arena_rows;
   auto& S = ix->scratch;
@@ -1354,31 +1672,44 @@ void tc_coarse(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   const CUtensorMap a_hi = make_tmap(v.vecs_hi, nrows, d, TC_BM), a_lo = make_tmap(v.vecs_lo, nrows, d, TC_BM);
   const CUtensorMap b16 = make_tmap(qhi, nq, d, 16), b32 = make_tmap(qhi, nq, d, 32), b64 = make_tmap(qhi, nq, d, 64), b128 = make_tmap(qhi, nq, d, 128);
   const CUtensorMap l16 = make_tmap(qlo, nq, d, 16), l32 = make_tmap(qlo, nq, d, 32), l64 = make_tmap(qlo, nq, d, 64), l128 = make_tmap(qlo, nq, d, 128);
-  const int grid = (int)std::min<int64_t>(g_num_sms, std::max(1, nitems));
+  const int grid = (int)std::min<int64_t>(num_sms, std::max(1, nitems));
   p.work_counter = work; p.split = 1; p.dense_accum = 0; p.add_norm = 1;
   ix->phase(IndexBase::PH_COARSE_SCAN, s);
   tc_scan_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(a_hi, a_hi, b16, b32, b64, b128, a_lo, l16, l32, l64, l128, b16, p);
   B200VS_CUDA(cudaGetLastError());
   ix->phase(IndexBase::PH_COARSE_FINAL, s);
-  if (nrows <= COARSE_FAST && nprobe <= nrows) {
-    // register-resident select (8 CTAs per SM), then the one-sort kernel for the queries it flagged (normally none)
+  const int maxw = std::max(2, next_pow2(nrows));
+  const size_t fast_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)maxw * 24;
+  if (nrows <= COARSE_FAST && nprobe <= nrows && fast_smem <= (size_t)TC_FAST_SMEM) {
+    // warp-select / block-re-score kernel for small tables, then the register-resident block select (8 CTAs per SM) for larger tables
+    // and for the queries the warp kernel flagged, then the one-sort kernel for what is still flagged (normally none)
+    int* redo0 = S.alloc<int>(nq);
     int* redo = S.alloc<int>(nq);
     const size_t qsm = ((size_t)d * 4 + 15) / 16 * 16;
     const int kpt = (nrows + SEL_THREADS - 1) / SEL_THREADS;
-#define B200VS_SEL(L2_, KPT_) tc_coarse_select_kernel<L2_, KPT_><<<(unsigned)nq, SEL_THREADS, qsm, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw, redo)
+    const int* redo_in = nullptr;
+    if (nrows <= 1024 && 2 * nprobe <= HC_MAXW) {
+#define B200VS_HSEL(L2_, KPT_) tc_coarse_select_hybrid_kernel<L2_, KPT_><<<(unsigned)nq, HC_THREADS, 0, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw, redo0)
+      if (nrows <= 256) { if (l2) B200VS_HSEL(true, 8); else B200VS_HSEL(false, 8); }
+      else if (nrows <= 512) { if (l2) B200VS_HSEL(true, 16); else B200VS_HSEL(false, 16); }
+      else { if (l2) B200VS_HSEL(true, 32); else B200VS_HSEL(false, 32); }
+#undef B200VS_HSEL
+      redo_in = redo0;
+      ix->launch_count(1);
+    }
+#define B200VS_SEL(L2_, KPT_) tc_coarse_select_kernel<L2_, KPT_><<<(unsigned)nq, SEL_THREADS, qsm, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw, redo, redo_in)
     if (kpt <= 4) { if (l2) B200VS_SEL(true, 4); else B200VS_SEL(false, 4); }
     else if (kpt <= 8) { if (l2) B200VS_SEL(true, 8); else B200VS_SEL(false, 8); }
     else if (kpt <= 16) { if (l2) B200VS_SEL(true, 16); else B200VS_SEL(false, 16); }
     else { if (l2) B200VS_SEL(true, 32); else B200VS_SEL(false, 32); }
 #undef B200VS_SEL
-    const int maxw = std::max(2, next_pow2(nrows));
-    const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)maxw * 24;
-    if (l2) tc_coarse_final_fast_kernel<true><<<(unsigned)nq, FIN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw, redo);
-    else tc_coarse_final_fast_kernel<false><<<(unsigned)nq, FIN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw, redo);
+    if (l2) tc_coarse_final_fast_kernel<true><<<(unsigned)nq, FIN_THREADS, fast_smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw, redo);
+    else tc_coarse_final_fast_kernel<false><<<(unsigned)nq, FIN_THREADS, fast_smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, maxw, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw, redo);
     ix->launch_count(1);
   } else {
     const int pool = select_pool_cap(nprobe, SCAN_THREADS);
     const size_t smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_SEG * 4 + BlockSelect::smem_bytes(pool);
+    if (smem > 160 * 1024) fail(B200VS_EILLEGAL_PARAMETERS, "coarse quantiser: dimension / nprobe too large for one SM's shared memory");
     if (l2) tc_coarse_final_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw);
     else tc_coarse_final_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem, s>>>(dense, nrows, nrows, qnorm, v.max_norm, q, v.vecs, d, nprobe, pool, v.id_offset, v.api_scores ? 1 : 0, out_probes, out_raw);
   }

@@ -1,0 +1,87 @@
+// warp_select.cuh — warp-level selection primitives: one warp finishes one query with no block barrier.
+//
+// The per-query finish work of the tile path (capture threshold, window select + exact re-score, coarse probe
+// selection) handles a few hundred keys per query.  A 256-thread CTA per query spends its time in __syncthreads
+// (radix passes, bitonic stages); a warp does the same selection with shuffles / ballots and a warp-private
+// shared-memory histogram, so an SM keeps dozens of queries in flight and a launch over N x 1024 queries (list-sharded
+// ranks finish every query of the global batch) costs about one wave.  These are the GPU form of the per-query heaps of
+// the reference path (faiss HeapBlockResultHandler behind IndexIVF::search, src/vector/vector_index_ivf_flat.cc:247-251).
+#pragma once
+#include "common.cuh"
+
+namespace b200vs {
+
+constexpr int WS_BINS = 512;  // histogram bins per narrowing step (9 bits), warp-private
+
+// k-th smallest (k >= 1; at least k keys are visited) of the keys the warp's lanes enumerate through `for_each`
+// (for_each(f) calls f(key) once per live key of THIS lane).  Range-normalised radix select: bin = (key - lo) >> shift
+// over the live range [lo, hi], narrow to the bin that holds the k-th key, repeat until bins are one key wide.
+// c_le = number of keys <= the result when it is known exactly, else k + 1.  All 32 lanes call; `hist` is a
+// warp-private int[WS_BINS].
+template <class ForEach>
+__device__ __forceinline__ uint32_t warp_kth_key(int k, int* hist, ForEach for_each, int& c_le) {
+  const int lane = threadIdx.x & 31;
+  uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+  for_each([&](uint32_t key) { mn = min(mn, key); mx = max(mx, key); });
+  uint32_t lo = __reduce_min_sync(0xffffffffu, mn), hi = __reduce_max_sync(0xffffffffu, mx);
+  int kk = k;
+  c_le = k + 1;
+  for (;;) {
+    const uint32_t range = hi - lo;
+    if (range == 0) return lo;  // every remaining key is equal
+    const int bits = 32 - __clz(range);
+    const int shift = max(0, bits - 9);
+    for (int i = lane; i < WS_BINS; i += 32) hist[i] = 0;
+    __syncwarp();
+    for_each([&](uint32_t key) { if (key >= lo && key <= hi) atomicAdd(&hist[(key - lo) >> shift], 1); });
+    __syncwarp();
+    constexpr int PER = WS_BINS / 32;
+    int loc[PER], sum = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { loc[j] = hist[lane * PER + j]; sum += loc[j]; }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const int before = incl - sum;
+    const bool mine = before < kk && kk <= incl;  // exactly one lane
+    int bin = 0, nk = 0, cle = 0;
+    if (mine) {
+      int acc = before;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        if (acc < kk && kk <= acc + loc[j]) { bin = lane * PER + j; nk = kk - acc; cle = (k - kk) + acc + loc[j]; }
+        acc += loc[j];
+      }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    nk = __shfl_sync(0xffffffffu, nk, src);
+    cle = __shfl_sync(0xffffffffu, cle, src);
+    const uint32_t nlo = lo + ((uint32_t)bin << shift);
+    hi = min(hi, nlo + ((1u << shift) - 1u));
+    lo = nlo;
+    kk = nk;
+    __syncwarp();
+    if (shift == 0) { c_le = cle; return lo; }
+  }
+}
+
+// Rank sort of m <= 64 (key, id) pairs held in warp-private shared memory: returns through `emit(rank, index)` for
+// every entry (rank = position in ascending (key, id) order; equal pairs keep their index order).
+template <class Emit>
+__device__ __forceinline__ void warp_rank_sort(const uint32_t* kd, const long long* kid, int m, Emit emit) {
+  const int lane = threadIdx.x & 31;
+  for (int e = lane; e < m; e += 32) {
+    const uint32_t d0 = kd[e];
+    const long long i0 = kid[e];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const uint32_t dj = kd[j];
+      const long long ij = kid[j];
+      rank += (key_less(dj, ij, d0, i0) || (dj == d0 && ij == i0 && j < e)) ? 1 : 0;
+    }
+    emit(rank, e);
+  }
+}
+
+}  // namespace b200vs

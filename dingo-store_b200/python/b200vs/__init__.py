@@ -25,6 +25,10 @@ ABI_SYMBOLS = [
     "b200vs_save", "b200vs_load", "b200vs_export_lists", "b200vs_merge_topk_device", "b200vs_last_search_stats", "b200vs_last_phase_times", "b200vs_calc_distance",
     "b200vs_scan_begin", "b200vs_scan_push", "b200vs_scan_finish", "b200vs_scan_abort", "b200vs_set_profiling",
     "b200vs_last_error", "b200vs_version",
+    "b200vs_add_with_ids_device", "b200vs_assign_device", "b200vs_reserve_lists",
+    "b200vs_shard_unique_id", "b200vs_shard_create", "b200vs_shard_destroy", "b200vs_shard_list_range", "b200vs_shard_train",
+    "b200vs_shard_broadcast_state", "b200vs_shard_add", "b200vs_shard_add_device", "b200vs_shard_plan_add_device",
+    "b200vs_shard_plan_commit", "b200vs_shard_search", "b200vs_shard_search_device",
 ]
 
 
@@ -95,6 +99,22 @@ def lib():
     L.b200vs_set_profiling.argtypes = [vp, ctypes.c_int]
     L.b200vs_last_error.restype = ctypes.c_char_p
     L.b200vs_version.restype = ctypes.c_char_p
+    L.b200vs_add_with_ids_device.argtypes = [vp, i64, vp, vp, vp, ctypes.c_int]
+    L.b200vs_assign_device.argtypes = [vp, i64, vp, vp]
+    L.b200vs_reserve_lists.argtypes = [vp, vp, i32]
+    L.b200vs_shard_unique_id.argtypes = [vp]
+    L.b200vs_shard_create.argtypes = [vp, i32, i32, vp, i32, ctypes.POINTER(vp)]
+    L.b200vs_shard_destroy.argtypes = [vp]
+    L.b200vs_shard_destroy.restype = None
+    L.b200vs_shard_list_range.argtypes = [vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+    L.b200vs_shard_train.argtypes = [vp, i64, vp]
+    L.b200vs_shard_broadcast_state.argtypes = [vp, i32]
+    L.b200vs_shard_add.argtypes = [vp, i64, vp, vp]
+    L.b200vs_shard_add_device.argtypes = [vp, i64, vp, vp]
+    L.b200vs_shard_plan_add_device.argtypes = [vp, i64, vp]
+    L.b200vs_shard_plan_commit.argtypes = [vp]
+    L.b200vs_shard_search.argtypes = [vp, i64, i64, vp, i32, ctypes.POINTER(SearchParams), vp, vp]
+    L.b200vs_shard_search_device.argtypes = [vp, i64, i64, vp, i32, ctypes.POINTER(SearchParams), vp, vp, vp]
     _lib = L
     return L
 
@@ -178,6 +198,16 @@ class Index:
 
     def upsert(self, x, ids):
         self.add(x, ids, upsert=True)
+
+    def add_device(self, n, x_dev_ptr, ids_dev_ptr, lists_dev_ptr=None, upsert=False):
+        _check(self.L.b200vs_add_with_ids_device(self.h, n, x_dev_ptr, ids_dev_ptr, lists_dev_ptr, int(upsert)))
+
+    def assign_device(self, n, x_dev_ptr, out_lists_dev_ptr):
+        _check(self.L.b200vs_assign_device(self.h, n, x_dev_ptr, out_lists_dev_ptr))
+
+    def reserve_lists(self, rows_per_list):
+        r = _i64(rows_per_list)
+        _check(self.L.b200vs_reserve_lists(self.h, r.ctypes.data, r.size))
 
     def delete(self, ids):
         ids = _i64(ids)
@@ -272,6 +302,75 @@ class Index:
 
     def load(self, path):
         _check(self.L.b200vs_load(self.h, path.encode()))
+
+
+class Shard:
+    """One rank of a list-sharded IVF_FLAT index (b200vs_shard_*).  `id_bytes`: the 128-byte rendezvous blob made by
+    Shard.unique_id() on rank 0 and distributed by the host (tests: torch.distributed broadcast)."""
+
+    @staticmethod
+    def unique_id():
+        buf = np.zeros(128, dtype=np.uint8)
+        _check(lib().b200vs_shard_unique_id(buf.ctypes.data))
+        return buf
+
+    def __init__(self, index, rank, world, id_bytes=None, lanes=2):
+        self.ix, self.rank, self.world = index, int(rank), int(world)
+        self.h = ctypes.c_void_p()
+        idb = np.ascontiguousarray(id_bytes, dtype=np.uint8) if id_bytes is not None else None
+        _check(lib().b200vs_shard_create(index.h, rank, world, idb.ctypes.data if idb is not None else None, lanes, ctypes.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().b200vs_shard_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def list_range(self, rank=None):
+        b, e = ctypes.c_int32(0), ctypes.c_int32(0)
+        _check(lib().b200vs_shard_list_range(self.h, self.rank if rank is None else rank, ctypes.byref(b), ctypes.byref(e)))
+        return b.value, e.value
+
+    def train(self, x):
+        x = _f32(x)
+        _check(lib().b200vs_shard_train(self.h, x.shape[0], x.ctypes.data))
+
+    def broadcast_state(self, root=0):
+        _check(lib().b200vs_shard_broadcast_state(self.h, root))
+
+    def add(self, x, ids):
+        x, ids = _f32(x), _i64(ids)
+        _check(lib().b200vs_shard_add(self.h, ids.size, x.ctypes.data if x.size else None, ids.ctypes.data if ids.size else None))
+
+    def add_device(self, n, x_dev_ptr, ids_dev_ptr):
+        _check(lib().b200vs_shard_add_device(self.h, n, x_dev_ptr, ids_dev_ptr))
+
+    def plan_add_device(self, n, x_dev_ptr):
+        _check(lib().b200vs_shard_plan_add_device(self.h, n, x_dev_ptr))
+
+    def plan_commit(self):
+        _check(lib().b200vs_shard_plan_commit(self.h))
+
+    def search(self, xq, k, seq=-1, **kw):
+        xq = _f32(xq)
+        nq = xq.shape[0]
+        sp, keep = make_search_params(**kw)
+        D = np.zeros((nq, k), dtype=np.float32)
+        I = np.full((nq, k), -1, dtype=np.int64)
+        _check(lib().b200vs_shard_search(self.h, seq, nq, xq.ctypes.data, k, ctypes.byref(sp), D.ctypes.data, I.ctypes.data))
+        return D, I
+
+    def search_raw(self, nq, xq_ptr, k, out_dist_ptr, out_ids_ptr, sp=None, seq=-1):
+        _check(lib().b200vs_shard_search(self.h, seq, nq, xq_ptr, k, ctypes.byref(sp) if sp is not None else None, out_dist_ptr, out_ids_ptr))
+
+    def search_device(self, nq, xq_dev_ptr, k, out_dist_dev_ptr, out_ids_dev_ptr, stream=None, sp=None, seq=-1):
+        _check(lib().b200vs_shard_search_device(self.h, seq, nq, xq_dev_ptr, k, ctypes.byref(sp) if sp is not None else None,
+                                                out_dist_dev_ptr, out_ids_dev_ptr, stream))
 
 
 def ivf_state_blob(centroids, metric):

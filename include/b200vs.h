@@ -145,6 +145,56 @@ int b200vs_coarse_device(b200vs_index* idx, int64_t nq, const float* xq_dev, int
 int b200vs_search_probes_device(b200vs_index* idx, int64_t nq, const float* xq_dev, int32_t k, const int64_t* probes_dev, int32_t nprobe,
                                 const b200vs_search_params* sp, float* out_dist_dev, int64_t* out_ids_dev, void* stream);
 
+/* ---- List-sharded multi-GPU deployment (one process per GPU) ----------------------------------------------
+ * One LOGICAL IVF_FLAT index over `world` GPUs of one box: the centroid table is replicated, rank r owns the inverted lists
+ * [r * ceil(nlist / world), (r + 1) * ceil(nlist / world)) (b200vs_shard_list_range) — equivalently Raft regions mapped to
+ * GPUs (src/vector/vector_index.h:54-55).  Every entry point below is COLLECTIVE: all ranks call it with the same
+ * arguments (except the rows each rank contributes to add).  Communication is NCCL over NVLink, resolved at run time
+ * (dlopen libnccl.so.2; override with B200VS_NCCL_LIB), one communicator per batch in flight.
+ *   shard_unique_id : rank 0 creates the rendezvous blob; the host passes it to the other ranks out of band (dingo-store: RPC)
+ *   shard_create    : wraps an (untrained or trained, still empty) IVF_FLAT index created with the GLOBAL nlist; `lanes` =
+ *                     batches that may be in flight (<= 0: 2)
+ *   shard_train     : distributed training — each rank clusters its rows into nlist / world centroids, one all-gather
+ *   shard_broadcast_state : or: replicate rank `root`'s trained state (b200vs_train / b200vs_set_trained_state there)
+ *   shard_add[_device]    : each rank passes the rows it holds; rows travel to the owner of their nearest centroid's list
+ *   shard_plan_add_device / shard_plan_commit : optional first pass of a bulk build (assignment only) that pre-sizes every
+ *                     owned list in one allocation — a 77 GB shard cannot afford list relocation or arena re-allocation
+ *   shard_search[_device] : all ranks pass the SAME batch.  Coarse quantiser on the rank's slice of the batch + all-gather of
+ *                     the probe table; tile scan of the owned probed lists; ONE all-gather of the packed per-shard top-k
+ *                     (16-byte (distance, id) records) + k-way merge (VectorIndexWrapper::MergeSearchResults,
+ *                     src/vector/vector_index.cc:1056-1108): every rank returns the full merged [nq, k].  The host-pointer
+ *                     variant uploads only the rank's slice of the batch and all-gathers the queries over NVLink.
+ *                     seq = batch sequence number: 0, 1, 2, ... the same on every rank, each used exactly once.  Batches are
+ *                     enqueued in seq order on every rank (concurrent caller threads simply take turns; the GPU work of
+ *                     up to `lanes` batches still overlaps), batch seq uses communicator seq % lanes.  seq < 0 = "next in
+ *                     call order" for single-threaded callers.  Results equal b200vs_search on the unsharded index. */
+#define B200VS_SHARD_ID_BYTES 128
+typedef struct b200vs_shard b200vs_shard;
+int b200vs_shard_unique_id(uint8_t id[B200VS_SHARD_ID_BYTES]);
+int b200vs_shard_create(b200vs_index* idx, int32_t rank, int32_t world, const uint8_t id[B200VS_SHARD_ID_BYTES], int32_t lanes,
+                        b200vs_shard** out);
+void b200vs_shard_destroy(b200vs_shard* shard);
+int b200vs_shard_list_range(b200vs_shard* shard, int32_t rank, int32_t* begin, int32_t* end);
+int b200vs_shard_train(b200vs_shard* shard, int64_t n, const float* x);
+int b200vs_shard_broadcast_state(b200vs_shard* shard, int32_t root);
+int b200vs_shard_add(b200vs_shard* shard, int64_t n, const float* x, const int64_t* ids);
+int b200vs_shard_add_device(b200vs_shard* shard, int64_t n, const float* x_dev, const int64_t* ids_dev);
+int b200vs_shard_plan_add_device(b200vs_shard* shard, int64_t n, const float* x_dev);
+int b200vs_shard_plan_commit(b200vs_shard* shard);
+int b200vs_shard_search(b200vs_shard* shard, int64_t seq, int64_t nq, const float* xq, int32_t k, const b200vs_search_params* sp,
+                        float* out_dist, int64_t* out_ids);
+int b200vs_shard_search_device(b200vs_shard* shard, int64_t seq, int64_t nq, const float* xq_dev, int32_t k,
+                               const b200vs_search_params* sp, float* out_dist_dev, int64_t* out_ids_dev, void* stream);
+
+/* Device-pointer write path of a single index (IVF_FLAT): rows and ids already on the index's device.  lists_dev (nullable)
+ * = the inverted list of every row when the caller has already assigned them (b200vs_assign_device); returns when done. */
+int b200vs_add_with_ids_device(b200vs_index* idx, int64_t n, const float* x_dev, const int64_t* ids_dev, const int64_t* lists_dev,
+                               int upsert);
+/* faiss quantizer->assign: nearest centroid of every (raw) row, out_lists_dev[n]; synchronous. */
+int b200vs_assign_device(b200vs_index* idx, int64_t n, const float* x_dev, int64_t* out_lists_dev);
+/* Pre-size every inverted list of an EMPTY trained IVF_FLAT index (rows_per_list[nlist], host) in one arena allocation. */
+int b200vs_reserve_lists(b200vs_index* idx, const int64_t* rows_per_list, int32_t nlist);
+
 /* Pairwise distance matrix, the UtilService path UtilServiceImpl::VectorCalcDistance (src/server/util_service.cc:45-92)
  * -> VectorIndexUtils::CalcDistanceEntry / CalcDistanceCore (src/vector/vector_index_utils.cc:48-124).  Host pointers,
  * row-major left [nl, dim], right [nr, dim]; out [nl, nr]: L2 -> squared L2, IP -> 1 - ip, COSINE -> 1 - ip of the
