@@ -5,6 +5,8 @@
   cfg2  IVF-Flat L2, 1M x 768, nlist 1024, nprobe 32, batch 256, top-10
   cfg3  IVF-PQ IP, N x 768, M = 96, nbits 8, nlist 2048, nprobe 64, batch 1024, top-100   (N scaled, see --pq-n)
   cfg4  HNSW cosine, N x 768, M = 16, efConstruction 200, efSearch 128, batch 512          (N scaled: host build)
+  cfg5  IVF-Flat L2, (rows-per-GPU x world) x 1536, nlist 2048 per GPU, nprobe 64, batch 4096, top-10, list-sharded over
+        the GPUs of the box through b200vs_shard_* — run under torchrun (BASELINE: 12.5 M rows per GPU x 8 GPUs = 100 M)
 Each line: device-resident QPS (CUDA events), e2e QPS through the host-pointer C ABI, parity with the oracle on a
 bounded sample, the dominant kernel's time from the library's profiling mode and the algorithmic figure of
 SURVEY.md §8(d).  Scaled sizes are stated in the line ("scaled_from").  Not part of the driver contract.
@@ -25,6 +27,7 @@ import torch  # noqa: E402
 
 import b200vs  # noqa: E402
 import oracle_lib  # noqa: E402
+import b200vs.shard as shard_host  # noqa: E402
 
 
 def peak():
@@ -206,6 +209,194 @@ def cfg4(o, cores, n):
             "build_seconds_engine": t_build, "build_seconds_oracle": t_oracle_build, "search_stats": st}
 
 
+def cfg5(o, cores, rows_per_gpu, steps=10, warmup=3, dim=1536, nlist_per_gpu=2048, nprobe=64, nq=4096, k=10, in_flight=2, verify=256, oracle_q=8):
+    """BASELINE config 5: one logical IVF-Flat index list-sharded over the world's GPUs behind b200vs_shard_*.
+    Build = distributed training, a planning pass that pre-sizes every owned list, then the add pass (rows generated on the
+    device, routed to their list owner over NCCL).  Every rank prints nothing; rank 0 returns the JSON line."""
+    import torch.distributed as dist
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    d, n = dim, rows_per_gpu
+    nlist = nlist_per_gpu * world
+    t0 = time.time()
+    ix = b200vs.Index(b200vs.IVF_FLAT, b200vs.L2, d, nlist=nlist, device=local)
+    idb = None
+    if world > 1:
+        t = torch.from_numpy(b200vs.Shard.unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
+        dist.broadcast(t, 0)
+        idb = t.cpu().numpy()
+    sh = b200vs.Shard(ix, rank, world, idb, lanes=in_flight)
+    chunk = 65536
+
+    def chunks():
+        g = torch.Generator(device=dev)
+        g.manual_seed(1234 + rank)
+        for a in range(0, n, chunk):
+            m = min(chunk, n - a)
+            yield a, torch.rand((m, d), generator=g, device=dev, dtype=torch.float32)
+
+    g0 = torch.Generator(device=dev)
+    g0.manual_seed(99 + rank)
+    ntrain = min(n, nlist_per_gpu * 64)
+    sh.train(torch.rand((ntrain, d), generator=g0, device=dev, dtype=torch.float32).cpu().numpy())
+    t_train = time.time() - t0
+    t1 = time.time()
+    for a, x in chunks():  # pass 1: assignment only -> per-list row counts
+        torch.cuda.synchronize()
+        sh.plan_add_device(x.shape[0], x.data_ptr())
+    sh.plan_commit()       # all-reduce of the counts, ONE arena allocation per rank
+    t_plan = time.time() - t1
+    t2 = time.time()
+    for a, x in chunks():  # pass 2: the same rows again, now stored on their list owner
+        gid = torch.arange(a + 1, a + 1 + x.shape[0], dtype=torch.int64, device=dev) + rank * n
+        torch.cuda.synchronize()
+        sh.add_device(x.shape[0], x.data_ptr(), gid.data_ptr())
+    t_add = time.time() - t2
+    del x
+    torch.cuda.empty_cache()
+    mem = ix.get_memory_size()
+    cnt = torch.tensor([ix.get_count()], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt)
+    # ---- timed search: device-resident queries, `in_flight` batches in flight ----
+    gq = torch.Generator(device=dev)
+    gq.manual_seed(4321)
+    qs = [torch.rand((nq, d), generator=gq, device=dev, dtype=torch.float32) for _ in range(2)]
+    L = in_flight
+    od = [torch.empty((nq, k), dtype=torch.float32, device=dev) for _ in range(L)]
+    oi = [torch.empty((nq, k), dtype=torch.int64, device=dev) for _ in range(L)]
+    sp, _keep = b200vs.make_search_params(nprobe=nprobe)
+    main = torch.cuda.Stream(device=dev)
+    sts = [torch.cuda.Stream(device=dev) for _ in range(L)]
+    torch.cuda.set_stream(main)
+    seq = [0]
+
+    def step(i, lanes):
+        ln = i % lanes
+        sh.search_device(nq, qs[i % 2].data_ptr(), k, od[ln].data_ptr(), oi[ln].data_ptr(), stream=sts[ln].cuda_stream, sp=sp, seq=seq[0])
+        seq[0] += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(nsteps, lanes):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for st in sts[:lanes]:
+            st.wait_event(e0)
+        for i in range(nsteps):
+            step(i, lanes)
+        for st in sts[:lanes]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+        e1.record(main)
+        barrier()
+        return e0.elapsed_time(e1)
+
+    for i in range(max(warmup, 2 * L)):
+        step(i, L)
+    barrier()
+    ms = timed(steps, L)
+    ms1 = timed(steps, 1)
+    # e2e through the host-pointer collective call
+    qh = [q.cpu().pin_memory() for q in qs]
+    hd = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    hi = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    for i in range(2):
+        sh.search_raw(nq, qh[i % 2].data_ptr(), k, hd.data_ptr(), hi.data_ptr(), sp=sp, seq=seq[0]); seq[0] += 1
+    barrier()
+    tt = time.perf_counter()
+    for i in range(steps):
+        sh.search_raw(nq, qh[i % 2].data_ptr(), k, hd.data_ptr(), hi.data_ptr(), sp=sp, seq=seq[0]); seq[0] += 1
+    barrier()
+    e2e_ms = (time.perf_counter() - tt) * 1e3
+    tm = torch.tensor([ms, ms1, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms, ms1, e2e_ms = tm.tolist()
+    # roofline of the list scan on this rank (profiling pass, never part of the timed numbers)
+    ix.set_profiling(True)
+    sh.search_device(nq, qs[0].data_ptr(), k, od[0].data_ptr(), oi[0].data_ptr(), stream=sts[0].cuda_stream, sp=sp, seq=seq[0]); seq[0] += 1
+    torch.cuda.synchronize()
+    st = ix.stats()
+    ph = ix.phase_times()
+    ix.set_profiling(False)
+    alg = st[4] * (d * 4 + 8)
+    roof = torch.tensor([alg / max(st[3], 1), st[3] / 1e6, float(st[2])], dtype=torch.float64, device=dev)
+    roofs = [torch.zeros_like(roof) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(roofs, roof)
+    else:
+        roofs = [roof]
+    # ---- verification 1: tile path vs the exact FP32 scan path (different kernels) on `verify` queries, full scale ----
+    xq = qh[0].numpy()[:verify].copy()
+    Dt, It = sh.search(xq, k, seq=seq[0], nprobe=nprobe); seq[0] += 1
+    De, Ie = sh.search(xq, k, seq=seq[0], nprobe=nprobe, exact_only=True); seq[0] += 1
+    # ---- verification 2: the CPU oracle on the lists the first `oracle_q` queries probe (exported list by list) ----
+    cent = ix.get_trained_state()[32:].view(np.float32).reshape(nlist, d)
+    xo = xq[:oracle_q]
+    # lists worth exporting: the exact top-(nprobe + 8) centroids of each query (a few extra: rounding at the boundary is harmless)
+    dd = ((xo[:, None, :].astype(np.float64) - cent[None, :, :].astype(np.float64)) ** 2).sum(-1)
+    pls = set(np.unique(np.argsort(dd, axis=1, kind="stable")[:, :nprobe + 8]).tolist())
+    b, e = sh.list_range()
+    off = np.zeros(nlist + 1, np.int64)
+    vs, idl = [], []
+    for l in range(nlist):
+        if b <= l < e and l in pls:
+            v, i_ = ix.export_list(l)
+            vs.append(v); idl.append(i_)
+            off[l + 1] = off[l] + v.shape[0]
+        else:
+            off[l + 1] = off[l]
+    lx = np.concatenate(vs, 0) if vs else np.zeros((0, d), np.float32)
+    lids = np.concatenate(idl, 0) if idl else np.zeros(0, np.int64)
+    threads = max(1, cores // world)
+    tt = time.time()
+    Do, Io = o.ivfflat_search(oracle_lib.L2, cent, off, lx, lids, xo, k, nprobe, nthreads=min(threads, oracle_q))
+    cpu_s = time.time() - tt
+    if world > 1:
+        gd = [torch.empty((oracle_q, k), dtype=torch.float32, device=dev) for _ in range(world)]
+        gi = [torch.empty((oracle_q, k), dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(gd, torch.from_numpy(Do).to(dev))
+        dist.all_gather(gi, torch.from_numpy(Io).to(dev))
+        Dm, Im = shard_host.merge_topk(torch.stack(gd).cpu().numpy(), torch.stack(gi).cpu().numpy(), k)
+        cs = torch.tensor([cpu_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(cs, op=dist.ReduceOp.MAX)
+        cpu_s = float(cs.item())
+    else:
+        Dm, Im = Do, Io
+    line = None
+    if rank == 0:
+        fr = [float(r[0]) / peak() for r in roofs]
+        line = {"config": f"cfg5 IVF-Flat L2 {n * world}x{d} ({n} rows per GPU x {world} GPUs), nlist={nlist} ({nlist_per_gpu} per GPU), nprobe={nprobe}, batch={nq}, top-{k}, list-sharded (b200vs_shard_*)",
+                "scaled_from": None if (n == 12_500_000 and world == 8) else "100M x 1536 over 8 GPUs (12.5 M rows per GPU)",
+                "assumptions": "nlist / nprobe are not given in BASELINE.json: 16384 / 64 at 8 GPUs (SURVEY 8d); synthetic U[0,1) rows generated on the device",
+                "n_gpus": world, "rows_total": int(cnt.item()), "index_bytes_per_gpu": mem,
+                "qps_device": nq * steps / (ms / 1e3), "ms_per_batch_device": ms / steps, "batches_in_flight": L,
+                "qps_single_stream": nq * steps / (ms1 / 1e3), "qps_e2e": nq * steps / (e2e_ms / 1e3), "ms_per_batch_e2e": e2e_ms / steps,
+                "roofline_per_rank": {"bound": "hbm", "kernel": "tc_scan_kernel capture pass", "achieved_gbs": [float(r[0]) for r in roofs], "kernel_ms": [float(r[1]) for r in roofs],
+                                      "peak": peak(), "frac": fr, "frac_min": min(fr), "frac_max": max(fr), "fallback_queries": [int(r[2]) for r in roofs],
+                                      "algorithmic_bytes_rank0": alg},
+                "phase_ms_rank0": {a: round(v, 4) for a, v in ph.items()},
+                "verify_tile_vs_exact_scan": {"queries": int(verify), "ids_bit_exact": bool(np.array_equal(It, Ie)),
+                                              "dist_bit_exact": bool(np.array_equal(Dt.view(np.uint32), De.view(np.uint32)))},
+                "verify_vs_oracle": {"queries": int(oracle_q), "ids_bit_exact": bool(np.array_equal(It[:oracle_q], Im)),
+                                     "dist_bit_exact": bool(np.array_equal(Dt[:oracle_q].view(np.uint32), Dm.view(np.uint32))),
+                                     "recall_at_10": float(np.mean([len(set(a_) & set(b_)) / k for a_, b_ in zip(It[:oracle_q], Im)])),
+                                     "how": "CPU oracle on every rank's probed lists (exported list by list), per-rank top-k merged with the MergeSearchResults rule"},
+                "cpu_baseline": {"qps": oracle_q / cpu_s, "cores": threads * world, "kind": "port",
+                                 "sample": f"{oracle_q} queries; each rank's oracle scans only the probed lists that rank owns ({threads} threads per rank, max over ranks)"},
+                "build_seconds": {"train": t_train, "plan_pass": t_plan, "add_pass": t_add}, "search_stats": st}
+    sh.close()
+    return line
+
+
 def cfg_calc(o, cores):
     """the UtilService distance matrix (VectorCalcDistance), 1024 x 1024 x 768, host pointers in and out."""
     nl = nr = 1024
@@ -260,18 +451,26 @@ def main():
     ap.add_argument("--configs", default="1,2,3,4")
     ap.add_argument("--pq-n", type=int, default=2_000_000)
     ap.add_argument("--hnsw-n", type=int, default=50_000)
+    ap.add_argument("--cfg5-rows", type=int, default=12_500_000, help="cfg5: database rows per GPU")
+    ap.add_argument("--cfg5-batch", type=int, default=4096)
+    ap.add_argument("--cfg5-steps", type=int, default=10)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     o = oracle_lib.load()
     cores = os.cpu_count() or 1
     fns = {"1": lambda: cfg1(o, cores), "2": lambda: cfg2(o, cores), "3": lambda: cfg3(o, cores, a.pq_n), "4": lambda: cfg4(o, cores, a.hnsw_n),
-           "calc": lambda: cfg_calc(o, cores), "brute": lambda: cfg_brute(o, cores)}
+           "calc": lambda: cfg_calc(o, cores), "brute": lambda: cfg_brute(o, cores),
+           "5": lambda: cfg5(o, cores, a.cfg5_rows, steps=a.cfg5_steps, nq=a.cfg5_batch)}
+    rank = int(os.environ.get("RANK", 0))
     for c in a.configs.split(","):
         t0 = time.time()
         try:
             line = fns[c]()
         except Exception as e:  # keep going: one line per config
-            line = {"config": f"cfg{c}", "error": repr(e)}
+            import traceback
+            line = {"config": f"cfg{c}", "error": repr(e), "traceback": traceback.format_exc()[-1500:]}
+        if line is None or rank != 0:  # multi-rank configs: rank 0 prints
+            continue
         line["wall_seconds"] = time.time() - t0
         s = json.dumps(line)
         print(s, flush=True)

@@ -312,6 +312,15 @@ int b200vs_export_lists(b200vs_index* h, int64_t* list_off, float* vectors, uint
   return guarded([&]() -> int { get(h)->export_lists(list_off, vectors, codes, ids); return B200VS_OK; });
 }
 
+int b200vs_export_list(b200vs_index* h, int32_t list, int64_t cap, float* vectors, int64_t* ids, int64_t* count) {
+  return guarded([&]() -> int {
+    if (cap < 0) fail(B200VS_EILLEGAL_PARAMETERS, "bad capacity");
+    const int64_t n = get(h)->export_list(list, cap, vectors, ids);
+    if (count) *count = n;
+    return B200VS_OK;
+  });
+}
+
 int b200vs_merge_topk_device(int32_t device, int32_t nparts, int64_t nq, int32_t k, const float* parts_dist,
                              const int64_t* parts_ids, float* out_dist, int64_t* out_ids, void* stream) {
   return guarded([&]() -> int {

@@ -99,31 +99,12 @@ __device__ __forceinline__ float quad_distance(const float* __restrict__ x, cons
   const int nfull = d >> 4;
   const float* xp = x + 4 * t;
   const float* qp = q + 4 * t;
-  if (vec) {
-    // 16-byte aligned rows: batches of 8 independent 128-bit loads per operand are issued before the (strictly ordered)
-    // accumulation, so a quad keeps 8 x 64 B of its row in flight instead of one load per dependent step
-    int c = 0;
-    for (; c + 8 <= nfull; c += 8) {
-      float4 xv[8], qv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) xv[j] = *reinterpret_cast<const float4*>(xp + 16 * j);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) qv[j] = *reinterpret_cast<const float4*>(qp + 16 * j);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc4<L2>(a, xv[j], qv[j]);
-      xp += 128; qp += 128;
-    }
-    for (; c < nfull; ++c) {
-      acc4<L2>(a, *reinterpret_cast<const float4*>(xp), *reinterpret_cast<const float4*>(qp));
-      xp += 16; qp += 16;
-    }
-  } else {
-    for (int c = 0; c < nfull; ++c) {
-      const float4 xv = make_float4(xp[0], xp[1], xp[2], xp[3]);
-      const float4 qv = make_float4(qp[0], qp[1], qp[2], qp[3]);
-      acc4<L2>(a, xv, qv);
-      xp += 16; qp += 16;
-    }
+#pragma unroll 16
+  for (int c = 0; c < nfull; ++c) {
+    const float4 xv = ld_f4(xp, vec);
+    const float4 qv = ld_f4(qp, vec);
+    acc4<L2>(a, xv, qv);
+    xp += 16; qp += 16;
   }
   int rem = d & 15;
   int base = nfull << 4;

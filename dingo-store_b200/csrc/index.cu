@@ -540,6 +540,7 @@ struct IvfFlatIndex : IndexBase {
     return (int64_t)(vecs.cap * 4 + ids.cap * 8 + norms.cap * 4 + centroids.cap * 4);
   }
   void export_lists(int64_t* list_off, float* vectors, uint8_t*, int64_t* out_ids) override;
+  int64_t export_list(int list, int64_t cap, float* vectors, int64_t* out_ids) override;
 };
 
 void IvfFlatIndex::train(int64_t n, const float* x) {
@@ -845,6 +846,31 @@ void IvfFlatIndex::export_lists(int64_t* list_off, float* vectors, uint8_t*, int
     }
   }
   if (list_off) list_off[nlist] = o;
+}
+
+int64_t IvfFlatIndex::export_list(int list, int64_t cap, float* vectors, int64_t* out_ids) {
+  std::shared_lock<std::shared_mutex> rl(rw);
+  std::lock_guard<std::mutex> gl(gpu_mu);
+  if (list < 0 || list >= nlist) fail(B200VS_EILLEGAL_PARAMETERS, "list id out of range");
+  set_device();
+  quiesce();
+  const auto& m = L.lists[list];
+  std::vector<float> rowbuf;
+  if (vectors && m.len) {
+    rowbuf.resize((size_t)m.len * dim);
+    B200VS_CUDA(cudaMemcpy(rowbuf.data(), vecs.p + (size_t)m.off * dim, (size_t)m.len * dim * 4, cudaMemcpyDeviceToHost));
+  }
+  int64_t o = 0;
+  for (int p = 0; p < m.len; ++p) {
+    const int64_t id = L.h_ids[m.off + p];
+    if (id < 0) continue;
+    if (o < cap) {
+      if (out_ids) out_ids[o] = id;
+      if (vectors) memcpy(vectors + (size_t)o * dim, rowbuf.data() + (size_t)p * dim, (size_t)dim * 4);
+    }
+    ++o;
+  }
+  return o;
 }
 
 IndexBase* make_ivf_flat(b200vs_metric m, int d, const b200vs_params& p) { return new IvfFlatIndex(m, d, p); }

@@ -146,7 +146,7 @@ struct IndexBase {
   } scratch{this};
   int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // profiling only (one caller at a time): CUDA-event marks between the phases of a search, b200vs_last_phase_times
-  enum Phase { PH_COARSE_PREP = 0, PH_COARSE_SCAN, PH_COARSE_FINAL, PH_PLAN, PH_SAMPLE, PH_TAU, PH_CAPTURE, PH_FINAL, PH_FALLBACK, PH_OTHER, PH_COUNT };
+  enum Phase { PH_COARSE_PREP = 0, PH_COARSE_SCAN, PH_COARSE_FINAL, PH_PLAN, PH_SAMPLE, PH_TAU, PH_CAPTURE, PH_FINAL, PH_FALLBACK, PH_OTHER, PH_COMM, PH_MERGE, PH_COUNT };
   float phase_ms[PH_COUNT] = {0};
   std::vector<std::pair<int, cudaEvent_t>> phase_marks;
   void phase(int id, cudaStream_t s) {  // "phase id starts here"
@@ -240,6 +240,10 @@ struct IndexBase {
   virtual int64_t deleted_count() const { return 0; }
   virtual int64_t memory_size() const = 0;
   virtual void export_lists(int64_t* list_off, float* vectors, uint8_t* codes, int64_t* ids) = 0;
+  virtual int64_t export_list(int list, int64_t cap, float* vectors, int64_t* ids) {
+    (void)list; (void)cap; (void)vectors; (void)ids;
+    fail(B200VS_EVECTOR_NOT_SUPPORT, "single-list export only exists for IVF_FLAT");
+  }
   virtual void save(const std::string& path);
   virtual void load(const std::string& path);
 

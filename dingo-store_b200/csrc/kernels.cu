@@ -28,7 +28,11 @@ void run_scan(IndexBase* ix, const ScanJob& job, int64_t nq, const float* querie
 // exact re-run of the queries listed in qmap[0 .. *qcount) (device-side count; grid sized for nq_max)
 void run_scan_mapped(IndexBase* ix, const ScanJob& job, int64_t nq_max, const int* qmap, const int* qcount, const float* queries,
                      int k, float* out_dist, long long* out_ids, cudaStream_t s) {
-  run_scan_impl(ix, job, nq_max, queries, k, out_dist, nullptr, out_ids, nullptr, qmap, qcount, 8, s);
+  // few queries are ever re-run, but each one re-streams all its candidates: split a query over enough CTAs that a single
+  // flagged query of a large index (cfg5: 2.4 GB of probed rows) is not an 8-CTA, 50 ms affair
+  const double cand = job.mode == 0 ? (double)job.n : job.avg_candidates;
+  const int nsplit = (int)std::max(8.0, std::min(128.0, cand / 4096.0));
+  run_scan_impl(ix, job, nq_max, queries, k, out_dist, nullptr, out_ids, nullptr, qmap, qcount, nsplit, s);
 }
 
 static void run_scan_impl(IndexBase* ix, const ScanJob& job, int64_t nq, const float* queries, int k, float* out_dist,

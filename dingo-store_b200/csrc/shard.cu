@@ -304,18 +304,21 @@ void shard_search_stream(b200vs_shard* sh, b200vs_shard::SLane& L, int64_t nq, c
   long long* mine = L.probes.p + (size_t)per * r * nprobe;
   if (q1 - q0 < per) fill_ll_kernel<<<(unsigned)cdiv(per * nprobe, 256), 256, 0, s>>>(mine, per * nprobe, -1);
   if (q1 > q0) ix->coarse_probes_dev(q1 - q0, q + (size_t)q0 * d, nprobe, mine, s);
-  ix->phase(IndexBase::PH_OTHER, s);
+  ix->phase(IndexBase::PH_COMM, s);
   if (W > 1) B200VS_NCCL(nccl().AllGather(mine, L.probes.p, (size_t)per * nprobe, ncclInt64, L.comm, s));
+  ix->phase(IndexBase::PH_OTHER, s);
   // 2) tile scan of the probed lists this rank owns -> exact local top-k
   L.od.reserve((size_t)nq * k, 0, s);
   L.oi.reserve((size_t)nq * k, 0, s);
   ix->search_probes_prepared_dev(nq, q, k, L.probes.p, nprobe, sc, L.od.p, L.oi.p, s);
-  ix->phase(IndexBase::PH_OTHER, s);
   // 3) ONE all-gather of the packed per-shard top-k + merge
   const long long nk = (long long)nq * k;
   L.parts.reserve((size_t)W * nk, 0, s);
+  ix->phase(IndexBase::PH_MERGE, s);
   pack_topk_kernel<<<(unsigned)cdiv(nk, 256), 256, 0, s>>>(L.od.p, L.oi.p, nk, L.parts.p + (size_t)r * nk);
+  ix->phase(IndexBase::PH_COMM, s);
   if (W > 1) B200VS_NCCL(nccl().AllGather(L.parts.p + (size_t)r * nk, L.parts.p, (size_t)nk * sizeof(TopkRec), ncclUint8, L.comm, s));
+  ix->phase(IndexBase::PH_MERGE, s);
   if (W * k <= MERGE_MAX) {
     merge_packed_warp_kernel<<<(unsigned)cdiv(nq, MERGE_WARPS), MERGE_WARPS * 32, 0, s>>>(L.parts.p, W, nq, k, out_dist, out_ids);
   } else {  // wide merges: unpack and use the block merge kernel
@@ -325,6 +328,7 @@ void shard_search_stream(b200vs_shard* sh, b200vs_shard::SLane& L, int64_t nq, c
     launch_merge_api(W, nq, k, pd, pi, out_dist, out_ids, s);
   }
   B200VS_CUDA(cudaGetLastError());
+  ix->phase(IndexBase::PH_OTHER, s);
   ix->launch_count(3);
   if (!L.done) B200VS_CUDA(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
   B200VS_CUDA(cudaEventRecord(L.done, s));

@@ -15,7 +15,9 @@
 //   tc_compact_flags_kernel  list of uncertified queries for the exact re-run
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include <mutex>
 
 #include "scan_kernels.cuh"
@@ -808,7 +810,7 @@ tc_final_fast_kernel(const unsigned long long* __restrict__ cand, const int* __r
 constexpr int HF_THREADS = 128;
 constexpr int HF_STAGE = 512;   // captured keys staged in shared memory (the rest is re-read from global / L2 in every pass)
 constexpr int HF_MAXW = 256;
-constexpr int HF_ROW_BYTES = 24 * 1024;  // dynamic shared memory for the staged window rows (+ the query row)
+constexpr int HF_ROW_BYTES = 48 * 1024;  // dynamic shared memory for the staged window rows (+ the query row)
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -910,7 +912,7 @@ tc_final_hybrid_kernel(const unsigned long long* __restrict__ cand, const int* _
   if (threadIdx.x == 0) {
     const float tq = tau[qi];
     const float a_k = s_ak;
-    flags[qi] = ((total <= cap) && (tq == TC_INF || a_k + two_eps <= tq)) ? 0 : 1;
+    flags[qi] = (total <= cap ? 0 : 2) | ((tq == TC_INF || a_k + two_eps <= tq) ? 0 : 1);  // 1: threshold too tight, 2: capture overflow
     redo[qi] = 0;
   }
 }
@@ -1615,11 +1617,26 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   // 4) uncertified queries re-run on the exact scan (device-side count: blocks beyond it exit immediately)
   ScanJob job;
   job.l2 = l2; job.vecs = v.vecs; job.ids = v.ids; job.d = d; job.sc = &sc;
-  if (!v.flat) { job.mode = 1; job.probes = probes; job.nprobe = nprobe; job.list_off = v.list_off; job.list_len = v.list_len; }
+  if (!v.flat) {
+    job.mode = 1; job.probes = probes; job.nprobe = nprobe; job.list_off = v.list_off; job.list_len = v.list_len;
+    job.avg_candidates = v.nlist > 0 ? (double)v.arena_rows * nprobe / v.nlist : 0;
+  }
   else { job.mode = 0; job.n = v.arena_rows; }
   ix->phase(IndexBase::PH_FALLBACK, s);
   run_scan_mapped(ix, job, nq, qmap, qcount, q, k, out_dist, out_ids, s);
   ix->phase(IndexBase::PH_OTHER, s);
+  if (ix->profiling && getenv("B200VS_DEBUG_FLAGS")) {
+    std::vector<int> hf(nq), hc(nq);
+    std::vector<float> ht(nq);
+    B200VS_CUDA(cudaMemcpyAsync(hf.data(), flags, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    B200VS_CUDA(cudaMemcpyAsync(hc.data(), cand_cnt, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    B200VS_CUDA(cudaMemcpyAsync(ht.data(), tau, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    B200VS_CUDA(cudaStreamSynchronize(s));
+    long long tot = 0; int mx = 0, r1 = 0, r2 = 0, ninf = 0;
+    for (int64_t i = 0; i < nq; ++i) { tot += hc[i]; mx = std::max(mx, hc[i]); r1 += (hf[i] & 1); r2 += (hf[i] & 2) ? 1 : 0; ninf += std::isinf(ht[i]) ? 1 : 0; }
+    fprintf(stderr, "[b200vs] tc_search nq=%lld cap=%d captured avg=%.1f max=%d flagged: threshold=%d overflow=%d tau_inf=%d\n", (long long)nq, cap, (double)tot / nq, mx, r1, r2, ninf);
+    for (int64_t i = 0, shown = 0; i < nq && shown < 4; ++i) if (hf[i]) { fprintf(stderr, "[b200vs]   q=%lld flag=%d captured=%d tau=%g\n", (long long)i, hf[i], hc[i], ht[i]); ++shown; }
+  }
   if (ix->profiling) {
     int h = 0;
     B200VS_CUDA(cudaMemcpyAsync(&h, qcount, 4, cudaMemcpyDeviceToHost, s));

@@ -127,6 +127,11 @@ int b200vs_load(b200vs_index* idx, const char* path);
 int b200vs_export_lists(b200vs_index* idx, int64_t* list_off /*[nlist+1]*/, float* vectors /*[count,dim]*/,
                         uint8_t* codes /*[count,pq_m]*/, int64_t* ids /*[count]*/);
 
+/* One inverted list (live rows only, stored order): writes up to `cap` rows into vectors [cap, dim] / ids [cap] (either may
+ * be NULL) and the list's live row count into *count.  Lets a checker rebuild exactly the lists a query probes without
+ * copying a 77 GB shard to the host. */
+int b200vs_export_list(b200vs_index* idx, int32_t list, int64_t cap, float* vectors, int64_t* ids, int64_t* count);
+
 /* k-way merge of per-shard top-k, the engine's analogue of VectorIndexWrapper::MergeSearchResults
  * (src/vector/vector_index.cc:1056-1108).  parts_* are DEVICE arrays [nparts, nq, k] (API-semantics
  * distances ascending, id -1 padded) e.g. the output of one ncclAllGather; out_* DEVICE [nq,k]. */
@@ -229,7 +234,8 @@ int b200vs_last_search_stats(b200vs_index* idx, int64_t stats[8]);
 /* With profiling on: device milliseconds (CUDA events on the launch stream) the last search spent in each phase of the
  * IVF tile path: [0] coarse prep, [1] coarse scan, [2] coarse select + exact re-score, [3] work planning + query
  * gather, [4] sample pass, [5] thresholds, [6] list scan (capture), [7] final select + exact re-score, [8] exact
- * fallback for uncertified queries, [9] other.  Unused slots are 0. */
+ * fallback for uncertified queries, [9] other, [10] collectives of a sharded search (b200vs_shard_search*), [11] pack + merge of
+ * the per-shard top-k.  Unused slots are 0. */
 int b200vs_last_phase_times(b200vs_index* idx, float ms[16]);
 int b200vs_set_profiling(b200vs_index* idx, int on);
 
