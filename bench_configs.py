@@ -274,9 +274,13 @@ def cfg5(o, cores, rows_per_gpu, steps=10, warmup=3, dim=1536, nlist_per_gpu=204
     torch.cuda.set_stream(main)
     seq = [0]
 
+    host_ms = []
+
     def step(i, lanes):
         ln = i % lanes
+        th = time.perf_counter()
         sh.search_device(nq, qs[i % 2].data_ptr(), k, od[ln].data_ptr(), oi[ln].data_ptr(), stream=sts[ln].cuda_stream, sp=sp, seq=seq[0])
+        host_ms.append((time.perf_counter() - th) * 1e3)
         seq[0] += 1
 
     def barrier():
@@ -303,7 +307,9 @@ def cfg5(o, cores, rows_per_gpu, steps=10, warmup=3, dim=1536, nlist_per_gpu=204
         step(i, L)
     barrier()
     ms = timed(steps, L)
+    del host_ms[:]
     ms1 = timed(steps, 1)
+    host_enqueue_ms = float(np.median(host_ms)) if host_ms else None
     # e2e through the host-pointer collective call
     qh = [q.cpu().pin_memory() for q in qs]
     hd = torch.empty((nq, k), dtype=torch.float32).pin_memory()
@@ -330,10 +336,13 @@ def cfg5(o, cores, rows_per_gpu, steps=10, warmup=3, dim=1536, nlist_per_gpu=204
     alg = st[4] * (d * 4 + 8)
     roof = torch.tensor([alg / max(st[3], 1), st[3] / 1e6, float(st[2])], dtype=torch.float64, device=dev)
     roofs = [torch.zeros_like(roof) for _ in range(world)]
+    phs = [None] * world
     if world > 1:
         dist.all_gather(roofs, roof)
+        dist.all_gather_object(phs, {a: round(v, 3) for a, v in ph.items()})
     else:
         roofs = [roof]
+        phs = [ph]
     # ---- verification 1: tile path vs the exact FP32 scan path (different kernels) on `verify` queries, full scale ----
     xq = qh[0].numpy()[:verify].copy()
     Dt, It = sh.search(xq, k, seq=seq[0], nprobe=nprobe); seq[0] += 1
@@ -383,7 +392,7 @@ def cfg5(o, cores, rows_per_gpu, steps=10, warmup=3, dim=1536, nlist_per_gpu=204
                 "roofline_per_rank": {"bound": "hbm", "kernel": "tc_scan_kernel capture pass", "achieved_gbs": [float(r[0]) for r in roofs], "kernel_ms": [float(r[1]) for r in roofs],
                                       "peak": peak(), "frac": fr, "frac_min": min(fr), "frac_max": max(fr), "fallback_queries": [int(r[2]) for r in roofs],
                                       "algorithmic_bytes_rank0": alg},
-                "phase_ms_rank0": {a: round(v, 4) for a, v in ph.items()},
+                "phase_ms_rank0": {a: round(v, 4) for a, v in ph.items()}, "phase_ms_all_ranks": phs, "host_enqueue_ms_per_batch_median": host_enqueue_ms,
                 "verify_tile_vs_exact_scan": {"queries": int(verify), "ids_bit_exact": bool(np.array_equal(It, Ie)),
                                               "dist_bit_exact": bool(np.array_equal(Dt.view(np.uint32), De.view(np.uint32)))},
                 "verify_vs_oracle": {"queries": int(oracle_q), "ids_bit_exact": bool(np.array_equal(It[:oracle_q], Im)),

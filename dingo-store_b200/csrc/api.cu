@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <memory>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "index.h"
@@ -232,6 +233,110 @@ int b200vs_search_probes_device(b200vs_index* h, int64_t nq, const float* xq_dev
   });
 }
 
+}  // extern "C"
+
+namespace {
+
+// one host-pointer search: H2D, search, D2H, wait.  xq / outputs may be pinned staging (coalesced batches) or caller memory.
+void host_search_once(IndexBase* ix, int64_t nq, const float* xq, int k, const b200vs_search_params* sp, float* out_dist, int64_t* out_ids) {
+  std::shared_lock<std::shared_mutex> rl(ix->rw);
+  ix->set_device();
+  LaneGuard lane(ix, nullptr);  // a free lane on its own stream, so concurrent callers overlap
+  cudaStream_t s = lane.stream;
+  ix->reset_stats();
+  float* dq = ix->scratch.alloc<float>((size_t)nq * ix->dim);
+  float* dd = ix->scratch.alloc<float>((size_t)nq * k);
+  long long* di = ix->scratch.alloc<long long>((size_t)nq * k);
+  B200VS_CUDA(cudaMemcpyAsync(dq, xq, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice, s));
+  SearchCtx sc = make_ctx(ix, sp, s);
+  ix->search_dev(nq, dq, k, sc, dd, di, s);
+  ix->phases_finish(s);
+  B200VS_CUDA(cudaMemcpyAsync(out_dist, dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
+  B200VS_CUDA(cudaMemcpyAsync(out_ids, di, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s));
+  B200VS_CUDA(cudaStreamSynchronize(s));
+}
+
+bool coalesce_compatible(const CoalesceReq& a, const CoalesceReq& b) {
+  return a.k == b.k && a.sp.nprobe == b.sp.nprobe && a.sp.efsearch == b.sp.efsearch && a.sp.exact_only == b.sp.exact_only &&
+         a.sp.has_range == b.sp.has_range && (!a.sp.has_range || (a.sp.range_min == b.sp.range_min && a.sp.range_max == b.sp.range_max));
+}
+
+constexpr int64_t kCoalesceMaxReq = 64;     // requests at most this large join a shared batch
+constexpr int64_t kCoalesceMaxBatch = 4096; // queries per shared batch (the service limit, index_service.cc:50)
+
+// the leader's work: one batch for all requests in `batch` (>= 2 of them, compatible)
+void run_coalesced(IndexBase* ix, std::vector<CoalesceReq*>& batch) {
+  int64_t total = 0;
+  for (auto* r : batch) total += r->nq;
+  const int k = batch[0]->k, d = ix->dim;
+  // pinned staging owned by the process-wide pool of this index: queries in, results out (one H2D, one D2H of each kind)
+  const size_t qbytes = (size_t)total * d * 4, dbytes = (size_t)total * k * 4, ibytes = (size_t)total * k * 8;
+  const size_t need = qbytes + dbytes + ibytes + 64;
+  static thread_local void* pin = nullptr;
+  static thread_local size_t pin_cap = 0;
+  if (pin_cap < need) {
+    if (pin) cudaFreeHost(pin);
+    pin = nullptr; pin_cap = 0;
+    B200VS_CUDA(cudaHostAlloc(&pin, need * 2, cudaHostAllocDefault));
+    pin_cap = need * 2;
+  }
+  float* hq = reinterpret_cast<float*>(pin);
+  float* hd = reinterpret_cast<float*>(reinterpret_cast<char*>(pin) + ((qbytes + 15) & ~(size_t)15));
+  int64_t* hi = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(hd) + ((dbytes + 15) & ~(size_t)15));
+  int64_t off = 0;
+  for (auto* r : batch) { memcpy(hq + (size_t)off * d, r->xq, (size_t)r->nq * d * 4); off += r->nq; }
+  host_search_once(ix, total, hq, k, &batch[0]->sp, hd, hi);
+  off = 0;
+  for (auto* r : batch) {
+    memcpy(r->out_dist, hd + (size_t)off * k, (size_t)r->nq * k * 4);
+    memcpy(r->out_ids, hi + (size_t)off * k, (size_t)r->nq * k * 8);
+    off += r->nq;
+  }
+}
+
+int coalesced_search(IndexBase* ix, int64_t nq, const float* xq, int k, const b200vs_search_params* sp, float* out_dist, int64_t* out_ids) {
+  Coalescer& C = ix->coalescer;
+  CoalesceReq me;
+  me.nq = nq; me.xq = xq; me.k = k; me.out_dist = out_dist; me.out_ids = out_ids;
+  if (sp) me.sp = *sp;
+  std::unique_lock<std::mutex> lk(C.mu);
+  C.pending.push_back(&me);
+  while (!me.done) {
+    if (C.busy) { C.cv.wait(lk); continue; }
+    // become the leader: everything compatible with the oldest pending request, in arrival order
+    C.busy = true;
+    std::vector<CoalesceReq*> batch, rest;
+    int64_t total = 0;
+    for (auto* r : C.pending) {
+      if ((batch.empty() || coalesce_compatible(*batch[0], *r)) && total + r->nq <= kCoalesceMaxBatch) { batch.push_back(r); total += r->nq; }
+      else rest.push_back(r);
+    }
+    C.pending.swap(rest);
+    lk.unlock();
+    int rc = B200VS_OK;
+    std::string err;
+    try {
+      if (batch.size() == 1) host_search_once(ix, batch[0]->nq, batch[0]->xq, batch[0]->k, &batch[0]->sp, batch[0]->out_dist, batch[0]->out_ids);
+      else run_coalesced(ix, batch);
+    } catch (const StatusError& e) { rc = e.code; err = e.msg; }
+    catch (const std::exception& e) { rc = B200VS_EINTERNAL; err = e.what(); }
+    catch (...) { rc = B200VS_EINTERNAL; err = "unknown error"; }
+    C.batches.fetch_add(1);
+    C.requests.fetch_add((int64_t)batch.size());
+    lk.lock();
+    for (auto* r : batch) { r->rc = rc; r->err = err; r->done = true; }
+    C.busy = false;
+    C.cv.notify_all();
+  }
+  lk.unlock();
+  if (me.rc != B200VS_OK) g_last_error = me.err;
+  return me.rc;
+}
+
+}  // namespace
+
+extern "C" {
+
 int b200vs_search(b200vs_index* h, int64_t nq, const float* xq, int32_t k, const b200vs_search_params* sp, float* out_dist,
                   int64_t* out_ids) {
   return guarded([&]() -> int {
@@ -239,21 +344,21 @@ int b200vs_search(b200vs_index* h, int64_t nq, const float* xq, int32_t k, const
     check_search_args(ix, nq, xq, sp);
     if (k <= 0) return B200VS_OK;
     if (!out_ids || !out_dist) fail(B200VS_EILLEGAL_PARAMETERS, "null output");
-    std::shared_lock<std::shared_mutex> rl(ix->rw);
-    ix->set_device();
-    LaneGuard lane(ix, nullptr);  // host-pointer call: a free lane on its own stream, so concurrent callers overlap
-    cudaStream_t s = lane.stream;
-    ix->reset_stats();
-    float* dq = ix->scratch.alloc<float>((size_t)nq * ix->dim);
-    float* dd = ix->scratch.alloc<float>((size_t)nq * k);
-    long long* di = ix->scratch.alloc<long long>((size_t)nq * k);
-    B200VS_CUDA(cudaMemcpyAsync(dq, xq, (size_t)nq * ix->dim * 4, cudaMemcpyHostToDevice, s));
-    SearchCtx sc = make_ctx(ix, sp, s);
-    ix->search_dev(nq, dq, k, sc, dd, di, s);
-    ix->phases_finish(s);
-    B200VS_CUDA(cudaMemcpyAsync(out_dist, dd, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
-    B200VS_CUDA(cudaMemcpyAsync(out_ids, di, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, s));
-    B200VS_CUDA(cudaStreamSynchronize(s));
+    // small filter-free requests share batches with concurrent callers (the reference issues one query per pool task)
+    if (nq <= kCoalesceMaxReq && ix->coalescer.enabled.load() && !(sp && sp->sorted_ids) && !ix->profiling)
+      return coalesced_search(ix, nq, xq, k, sp, out_dist, out_ids);
+    host_search_once(ix, nq, xq, k, sp, out_dist, out_ids);
+    return B200VS_OK;
+  });
+}
+
+/* Request coalescing of b200vs_search (on by default): concurrent host-pointer calls of <= 64 queries without id-list filters
+ * are merged into shared batches.  stats (nullable): [0] batches run, [1] requests served through them. */
+int b200vs_set_coalescing(b200vs_index* h, int on, int64_t stats[2]) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    if (on >= 0) ix->coalescer.enabled.store(on ? 1 : 0);
+    if (stats) { stats[0] = ix->coalescer.batches.load(); stats[1] = ix->coalescer.requests.load(); }
     return B200VS_OK;
   });
 }

@@ -7,6 +7,7 @@
 
 #include "index.h"
 #include "ivf_common.h"
+#include "flat_small.cuh"
 #include "tc_scan.cuh"
 
 namespace b200vs {
@@ -334,6 +335,10 @@ struct FlatIndex : IndexBase {
       long long* probes = scratch.alloc<long long>(nq);
       B200VS_CUDA(cudaMemsetAsync(probes, 0, (size_t)nq * 8, s));
       tc_search(this, v, metric == B200VS_L2, nq, q, k, probes, 1, sc, od, oi, s);
+      return;
+    }
+    if (flat_small_eligible(nq, rows, dim, k, sc)) {  // one query per task is the reference's own shape: single-launch path
+      flat_small_search(this, metric == B200VS_L2, vecs.p, ids.p, rows, nq, q, k, sc, od, oi, s);
       return;
     }
     run_scan(this, job(sc), nq, q, k, od, nullptr, oi, nullptr, s);

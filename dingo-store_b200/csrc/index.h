@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
 #include <mutex>
@@ -106,6 +107,31 @@ struct Lane {
 };
 constexpr int kLanes = 8;
 
+// Request coalescing for host-pointer searches ("b200vs_search internally coalesces concurrent callers").  The
+// unchanged reference caller slices every batch into single-query tasks on a 16-thread pool (src/vector/vector_index.cc:54,
+// :244-271), so the plugin sees many concurrent nq = 1 calls.  Callers queue here; the one that finds no leader active
+// becomes the leader, takes every compatible pending request (same k / nprobe / efsearch / exact_only, no id filters) and
+// runs them as ONE batch — large enough batches reach the tensor-core tile path — then hands the results back.
+struct CoalesceReq {
+  int64_t nq = 0;
+  const float* xq = nullptr;
+  int k = 0;
+  b200vs_search_params sp{};
+  float* out_dist = nullptr;
+  int64_t* out_ids = nullptr;
+  int rc = 0;
+  std::string err;
+  bool done = false;
+};
+struct Coalescer {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<CoalesceReq*> pending;
+  bool busy = false;
+  std::atomic<int> enabled{1};
+  std::atomic<int64_t> batches{0}, requests{0};  // statistics: leader batches run / requests served through them
+};
+
 struct SearchCtx {  // resolved per-search parameters, device filter included
   int nprobe = 0;
   int efsearch = 0;
@@ -128,6 +154,7 @@ struct IndexBase {
   std::shared_mutex rw;  // readers = searches, writers = add/remove/train (reference RWLock)
   std::mutex gpu_mu;     // writers / maintenance (they also hold rw exclusively)
   Lane lanes[kLanes];
+  Coalescer coalescer;
   std::atomic<unsigned> lane_rr{0};
   std::mutex lane_pick_mu;
   unsigned long long lane_tick = 0;

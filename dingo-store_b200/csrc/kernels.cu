@@ -31,7 +31,8 @@ void run_scan_mapped(IndexBase* ix, const ScanJob& job, int64_t nq_max, const in
   // few queries are ever re-run, but each one re-streams all its candidates: split a query over enough CTAs that a single
   // flagged query of a large index (cfg5: 2.4 GB of probed rows) is not an 8-CTA, 50 ms affair
   const double cand = job.mode == 0 ? (double)job.n : job.avg_candidates;
-  const int nsplit = (int)std::max(8.0, std::min(128.0, cand / 4096.0));
+  int nsplit = (int)std::max(8.0, std::min(128.0, cand / 512.0));
+  nsplit = (int)std::max<int64_t>(8, std::min<int64_t>(nsplit, (64LL << 20) / std::max<int64_t>(1, nq_max * k)));  // partial-result workspace
   run_scan_impl(ix, job, nq_max, queries, k, out_dist, nullptr, out_ids, nullptr, qmap, qcount, nsplit, s);
 }
 
@@ -68,7 +69,8 @@ static void run_scan_impl(IndexBase* ix, const ScanJob& job, int64_t nq, const f
 
   const size_t smem1 = scan_smem_bytes(job.d, job.mode == 0 ? 1 : job.nprobe, cap);
   const size_t smem2 = BlockSelect::smem_bytes(cap);
-  const unsigned slots = qcount ? (unsigned)std::min<int64_t>(nq, 64) : (unsigned)nq;  // mapped launch: CTAs stride over the live slots
+  // mapped launch: a fixed budget of ~4 CTAs per SM strides over the live slots (the usual "nothing to redo" launch stays cheap)
+  const unsigned slots = qcount ? (unsigned)std::min<int64_t>(nq, std::max(1, 592 / nsplit)) : (unsigned)nq;
   dim3 grid(nsplit, slots);
   ScopedKernelTimer timer(ix, s, ix->profiling && job.dominant);
   if (job.l2) {

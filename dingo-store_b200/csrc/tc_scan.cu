@@ -472,6 +472,24 @@ tc_scan_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 __device__ uint32_t block_kth_key(const unsigned long long* keys, int n, int k);
 __device__ __forceinline__ float tc_eps(bool l2, float qnorm_sq, float max_norm, int d, bool split);
 
+// Capture threshold from the sampled k-th score tau.  The finish kernel certifies A_k + 2 eps <= T (A_k = k-th captured
+// score); a query that fails is re-run on the exact scan, and a single re-scanned query of a large shard stalls every rank
+// of a sharded batch for milliseconds.  Two cases:
+//   * at least TAU_SAFE sampled scores lie below tau - 2 eps: about TAU_SAFE * TC_SPAN / TC_SAMPLE rows do too, far more
+//     than k, so A_k < tau - 2 eps almost surely (fewer than k such rows would have to produce TAU_SAFE sample hits at a
+//     1 / 64 sampling rate: probability < 3e-4 even then) -> T = tau, the tightest capture set;
+//   * otherwise the k-th row may sit within 2 eps of tau: capture under T = tau + 2 eps, which makes the certification true
+//     by construction (A_k <= tau because the sample is a subset of the rows) at the price of a wider capture set — taken
+//     only while the predicted number of captures leaves headroom in the capture buffer.
+constexpr int TAU_SAFE = 3;
+template <class CountLE>
+__device__ __forceinline__ float tc_tau_with_margin(float tau, float two_eps, int cap, CountLE count_le) {
+  if (count_le(__fsub_rd(tau, two_eps)) >= TAU_SAFE) return tau;
+  const float lim = __fadd_ru(tau, two_eps);
+  const long long predicted = (long long)count_le(lim) * (TC_SPAN / TC_SAMPLE);
+  return predicted * 4 <= (long long)cap * 3 ? lim : tau;
+}
+
 constexpr int TAU_PL = 4096;  // (sample slot, column) pairs staged per query
 constexpr int TAU_SORT = 4096;  // sampled scores sorted in one shot when they fit
 
@@ -479,7 +497,7 @@ static __global__ void __launch_bounds__(SCAN_THREADS)
 tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos, const int* __restrict__ cnt,
               const int* __restrict__ item_off, const int* __restrict__ list_len, const TcItem* __restrict__ items, int nprobe,
               const float* __restrict__ sample, int srows, int k, int pool_cap, int l2, const float* __restrict__ qnorm,
-              float max_norm, int d, int margin, float* tau, const int* redo) {
+              float max_norm, int d, int margin, int cand_cap, float* tau, const int* redo) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ int s_np;
   const int q = blockIdx.x;
@@ -520,7 +538,23 @@ tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos,
     __syncthreads();
     const int nfin = s_fin;
     const uint32_t kth = nfin >= k ? block_kth_key(vals, nfin, k) : 0u;
-    if (threadIdx.x == 0) tau[q] = nfin >= k ? __fadd_rn(ord2f(kth), margin ? 2.f * tc_eps(l2 != 0, qnorm[q], max_norm, d, false) : 0.f) : TC_INF;
+    if (nfin < k) { if (threadIdx.x == 0) tau[q] = TC_INF; return; }
+    const float two_eps = 2.f * tc_eps(l2 != 0, qnorm[q], max_norm, d, false);
+    if (margin) { if (threadIdx.x == 0) tau[q] = __fadd_rn(ord2f(kth), two_eps); return; }  // dense samples: always
+    __shared__ int s_cle;
+    auto count_le = [&](float lim) {  // block-wide count of sampled scores <= lim (all threads call)
+      __syncthreads();
+      if (threadIdx.x == 0) s_cle = 0;
+      __syncthreads();
+      int c = 0;
+      for (int i = threadIdx.x; i < nfin; i += blockDim.x) c += ord2f((uint32_t)(vals[i] >> 32)) <= lim ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cle, c);
+      __syncthreads();
+      return s_cle;
+    };
+    const float t = tc_tau_with_margin(ord2f(kth), two_eps, cand_cap, count_le);
+    if (threadIdx.x == 0) tau[q] = t;
     return;
   }
   for (int base = 0; base < tot; base += blockDim.x) {
@@ -552,7 +586,8 @@ constexpr int WT_PAIRS = 64;
 static __global__ void __launch_bounds__(WT_WARPS * 32)
 tc_tau_warp_kernel(const long long* __restrict__ probes, const int* __restrict__ pos, const int* __restrict__ cnt,
                    const int* __restrict__ item_off, const int* __restrict__ list_len, const TcItem* __restrict__ items, int nprobe,
-                   const float* __restrict__ sample, int k, int nq, float* tau, int* redo) {
+                   const float* __restrict__ sample, int k, int nq, int l2, const float* __restrict__ qnorm, float max_norm, int d, int cap,
+                   float* tau, int* redo) {
   __shared__ int s_hist[WT_WARPS][WS_BINS];
   __shared__ int s_pair[WT_WARPS][WT_PAIRS];
   __shared__ uint32_t s_val[WT_WARPS][WT_PAIRS * TC_SAMPLE];
@@ -610,6 +645,8 @@ tc_tau_warp_kernel(const long long* __restrict__ probes, const int* __restrict__
     int c_le;
     const uint32_t* vals = s_val[warp];
     t = ord2f(warp_kth_key(k, s_hist[warp], [&](auto f) { for (int i = lane; i < nfin; i += 32) f(vals[i]); }, c_le));
+    t = tc_tau_with_margin(t, 2.f * tc_eps(l2 != 0, qnorm[q], max_norm, d, false), cap,
+                           [&](float lim) { int c = 0; for (int i = lane; i < nfin; i += 32) c += ord2f(vals[i]) <= lim ? 1 : 0; return __reduce_add_sync(0xffffffffu, c); });
   }
   if (lane == 0) tau[q] = t;
 }
@@ -1424,7 +1461,7 @@ static int64_t tc_sample_bound(const TcView& v, int64_t npairs) {  // spans are 
   const int64_t max_spans = (v.max_chunks_per_list + 3) / 4 + 1;
   return (npairs / TC_NQT + 1) * max_spans + (v.total_chunks + 3) / 4 + v.nlist;
 }
-static int tc_cand_cap(int k) { return std::min(16384, std::max(2048, next_pow2(128 * k))); }
+static int tc_cand_cap(int k) { return std::min(16384, std::max(4096, next_pow2(256 * k))); }
 
 // Per-device one-time setup: cudaFuncSetAttribute applies to the CURRENT device only, and one process may hold indexes
 // on several GPUs (b200vs_params.device), so the opt-in shared-memory limits are raised once per device ordinal.
@@ -1576,10 +1613,10 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   int* redo = S.alloc<int>(nq);
   const size_t tau_smem = (size_t)TAU_PL * 8 + std::max(sel_smem, (size_t)TAU_SORT * 8);
   if (srows == TC_SAMPLE) {  // warp per query; the block kernel only redoes queries with more sampled spans than a warp stages
-    tc_tau_warp_kernel<<<(unsigned)cdiv(nq, WT_WARPS), WT_WARPS * 32, 0, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, k, (int)nq, tau, redo);
-    tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, tau_smem, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, srows, k, pool, l2 ? 1 : 0, P.qnorm, v.max_norm, d, 0, tau, redo);
+    tc_tau_warp_kernel<<<(unsigned)cdiv(nq, WT_WARPS), WT_WARPS * 32, 0, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, k, (int)nq, l2 ? 1 : 0, P.qnorm, v.max_norm, d, cap, tau, redo);
+    tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, tau_smem, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, srows, k, pool, l2 ? 1 : 0, P.qnorm, v.max_norm, d, 0, cap, tau, redo);
   } else {
-    tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, tau_smem, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, srows, k, pool, l2 ? 1 : 0, P.qnorm, v.max_norm, d, 1, tau, nullptr);
+    tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, tau_smem, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, srows, k, pool, l2 ? 1 : 0, P.qnorm, v.max_norm, d, 1, cap, tau, nullptr);
   }
   // 2) capture pass: stream every probed list chunk once, keep rows under the threshold
   p.mode = 1; p.work_counter = P.work + 1;

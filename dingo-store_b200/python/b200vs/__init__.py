@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "b200vs_save", "b200vs_load", "b200vs_export_lists", "b200vs_merge_topk_device", "b200vs_last_search_stats", "b200vs_last_phase_times", "b200vs_calc_distance",
     "b200vs_scan_begin", "b200vs_scan_push", "b200vs_scan_finish", "b200vs_scan_abort", "b200vs_set_profiling",
     "b200vs_last_error", "b200vs_version",
-    "b200vs_add_with_ids_device", "b200vs_assign_device", "b200vs_reserve_lists", "b200vs_export_list",
+    "b200vs_add_with_ids_device", "b200vs_assign_device", "b200vs_reserve_lists", "b200vs_export_list", "b200vs_set_coalescing",
     "b200vs_shard_unique_id", "b200vs_shard_create", "b200vs_shard_destroy", "b200vs_shard_list_range", "b200vs_shard_train",
     "b200vs_shard_broadcast_state", "b200vs_shard_add", "b200vs_shard_add_device", "b200vs_shard_plan_add_device",
     "b200vs_shard_plan_commit", "b200vs_shard_search", "b200vs_shard_search_device",
@@ -103,6 +103,7 @@ def lib():
     L.b200vs_assign_device.argtypes = [vp, i64, vp, vp]
     L.b200vs_reserve_lists.argtypes = [vp, vp, i32]
     L.b200vs_export_list.argtypes = [vp, i32, i64, vp, vp, ctypes.POINTER(i64)]
+    L.b200vs_set_coalescing.argtypes = [vp, ctypes.c_int, ctypes.POINTER(i64 * 2)]
     L.b200vs_shard_unique_id.argtypes = [vp]
     L.b200vs_shard_create.argtypes = [vp, i32, i32, vp, i32, ctypes.POINTER(vp)]
     L.b200vs_shard_destroy.argtypes = [vp]
@@ -297,6 +298,12 @@ class Index:
                                           codes.ctypes.data if codes is not None and codes.size else None,
                                           ids.ctypes.data if ids.size else None))
         return off, vec, codes, ids
+
+    def coalescing(self, on=-1):
+        """Switch (1 / 0) or just read (-1) request coalescing; returns (batches run, requests served)."""
+        a = (ctypes.c_int64 * 2)()
+        _check(self.L.b200vs_set_coalescing(self.h, on, ctypes.byref(a)))
+        return int(a[0]), int(a[1])
 
     def export_list(self, list_id):
         """(vectors [n, dim], ids [n]) of one inverted list (live rows, stored order)."""

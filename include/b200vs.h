@@ -97,6 +97,13 @@ int b200vs_remove_ids(b200vs_index* idx, int64_t n, const int64_t* ids, int64_t*
  * xq row-major [nq,dim] RAW; out_dist [nq,k], out_ids [nq,k]. */
 int b200vs_search(b200vs_index* idx, int64_t nq, const float* xq, int32_t k, const b200vs_search_params* sp,
                   float* out_dist, int64_t* out_ids);
+/* b200vs_search coalesces concurrent callers: the unchanged reference slices every batch into one-query tasks
+ * on its 16-thread pool (src/vector/vector_index.cc:54, :244-271), so the plugin sees many concurrent nq = 1 calls.  Calls
+ * of <= 64 queries without id-list filters queue inside the library; the caller that finds no leader active runs every
+ * compatible pending request (same k / nprobe / efsearch / exact_only / id range) as ONE batch and hands the results back.
+ * on: 1 / 0 switch it, < 0 only reads; stats (nullable): [0] batches run, [1] requests served through them. */
+int b200vs_set_coalescing(b200vs_index* idx, int on, int64_t stats[2]);
+
 /* Same, with xq / out_dist / out_ids DEVICE pointers on the index's device; enqueued on `stream`
  * (a cudaStream_t) and NOT synchronised when it returns.  stream == NULL runs the search on a library-owned stream and
  * returns only when the results are complete (it does not touch the legacy default stream).  The same holds for
