@@ -390,6 +390,21 @@ int b200vs_range_search(b200vs_index* h, int64_t nq, const float* xq, float radi
   });
 }
 
+int b200vs_reconstruct(b200vs_index* h, int64_t n, const int64_t* ids, float* out, uint8_t* found) {
+  return guarded([&]() -> int {
+    IndexBase* ix = get(h);
+    if (n <= 0) return B200VS_OK;
+    if (!ids || !out) fail(B200VS_EILLEGAL_PARAMETERS, "null ids / output");
+    ix->reconstruct(n, ids, out, found);
+    return B200VS_OK;
+  });
+}
+int b200vs_sub_type(b200vs_index* h) {
+  int r = -1;
+  guarded([&]() -> int { IndexBase* ix = get(h); std::shared_lock<std::shared_mutex> rl(ix->rw); r = ix->sub_type(); return B200VS_OK; });
+  return r;
+}
+
 int b200vs_count(b200vs_index* h, int64_t* count) {
   return guarded([&]() -> int { IndexBase* ix = get(h); std::shared_lock<std::shared_mutex> rl(ix->rw); if (count) *count = ix->count(); return B200VS_OK; });
 }

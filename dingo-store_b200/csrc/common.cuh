@@ -99,12 +99,22 @@ __device__ __forceinline__ float quad_distance(const float* __restrict__ x, cons
   const int nfull = d >> 4;
   const float* xp = x + 4 * t;
   const float* qp = q + 4 * t;
-#pragma unroll 16
-  for (int c = 0; c < nfull; ++c) {
-    const float4 xv = ld_f4(xp, vec);
-    const float4 qv = ld_f4(qp, vec);
-    acc4<L2>(a, xv, qv);
-    xp += 16; qp += 16;
+  if (vec) {  // 16-byte aligned rows: no branch inside the loop, so the unrolled body issues its 128-bit loads back to back
+#pragma unroll 8
+    for (int c = 0; c < nfull; ++c) {
+      const float4 xv = *reinterpret_cast<const float4*>(xp);
+      const float4 qv = *reinterpret_cast<const float4*>(qp);
+      acc4<L2>(a, xv, qv);
+      xp += 16; qp += 16;
+    }
+  } else {
+#pragma unroll 4
+    for (int c = 0; c < nfull; ++c) {
+      const float4 xv = make_float4(xp[0], xp[1], xp[2], xp[3]);
+      const float4 qv = make_float4(qp[0], qp[1], qp[2], qp[3]);
+      acc4<L2>(a, xv, qv);
+      xp += 16; qp += 16;
+    }
   }
   int rem = d & 15;
   int base = nfull << 4;

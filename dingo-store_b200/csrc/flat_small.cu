@@ -18,7 +18,7 @@
 
 namespace b200vs {
 
-constexpr int FS_THREADS = 256;
+constexpr int FS_THREADS = 512;
 constexpr int FS_PAIRS = 3072;  // (key, id) pairs a CTA holds in shared memory: its slice's rows, later the per-slice lists it merges
 constexpr int FS_CT = 128;      // entries the rank sort holds (k <= FS_CT / 2)
 
@@ -49,7 +49,7 @@ __device__ __forceinline__ long long warp_min_ll(long long v) {
 // Mass ties (more than FS_CT pairs share the k-th key: duplicated vectors): the pairs strictly below kth are kept and the
 // open slots are filled with the smallest ids among the tied pairs, one warp-min per slot — same (key, id) order, no limit.
 template <class Emit>
-__device__ __forceinline__ void fs_topk_warp(const uint32_t* kd, const long long* id, int n, int k, int* hist, uint32_t* ckd, long long* cid, Emit emit) {
+__device__ __forceinline__ int fs_topk_warp(const uint32_t* kd, const long long* id, int n, int k, int* hist, uint32_t* ckd, long long* cid, Emit emit) {
   const int lane = threadIdx.x & 31;
   uint32_t kth = 0xFFFFFFFFu;
   if (n > k) {
@@ -59,7 +59,7 @@ __device__ __forceinline__ void fs_topk_warp(const uint32_t* kd, const long long
   int m = 0;
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
-    const bool in = i < n && kd[i] <= kth;
+    const bool in = i < n && kd[i] <= kth && !(kd[i] == KEY_SENTINEL_D && id[i] == KEY_SENTINEL_ID);  // empty slots never surface
     const unsigned msk = __ballot_sync(0xffffffffu, in);
     const int p = m + __popc(msk & ((1u << lane) - 1u));
     if (in && p < FS_CT) { ckd[p] = kd[i]; cid[p] = id[i]; }
@@ -87,6 +87,7 @@ __device__ __forceinline__ void fs_topk_warp(const uint32_t* kd, const long long
     __syncwarp();
   }
   warp_rank_sort(ckd, cid, m, [&](int rank, int e) { if (rank < k) emit(rank, ckd[e], cid[e]); });
+  return min(m, k);
 }
 
 template <bool L2>
@@ -114,15 +115,19 @@ static __global__ void __launch_bounds__(FS_THREADS) flat_small_kernel(const FsA
     if (valid) { id = a.ids[row]; valid = id >= 0 && filter_pass(a.filt, id); }
     if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
     const float v = quad_distance<L2>(a.vecs + (size_t)(valid ? row : r0) * d, qs, d, t, vec);
-    if (valid && t == 0) { const int p = atomicAdd(&s_n, 1); s_kd[p] = f2ord(L2 ? v : -v); s_id[p] = id; }
+    const unsigned wm = __ballot_sync(0xffffffffu, valid && t == 0);  // one shared-memory atomic per warp
+    int wbase = 0;
+    if ((threadIdx.x & 31) == 0) wbase = atomicAdd(&s_n, __popc(wm));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (valid && t == 0) { const int p = wbase + __popc(wm & ((1u << (threadIdx.x & 31)) - 1u)); s_kd[p] = f2ord(L2 ? v : -v); s_id[p] = id; }
   }
   __syncthreads();
   uint32_t* pk = a.part_kd + ((size_t)qi * nslices + slice) * k;
   long long* pi = a.part_id + ((size_t)qi * nslices + slice) * k;
   if (threadIdx.x < 32) {
     const int n = s_n;
-    fs_topk_warp(s_kd, s_id, n, k, s_hist, s_ckd, s_cid, [&](int rank, uint32_t kd, long long id) { pk[rank] = kd; pi[rank] = id; });
-    for (int i = min(n, k) + (int)threadIdx.x; i < k; i += 32) { pk[i] = KEY_SENTINEL_D; pi[i] = KEY_SENTINEL_ID; }
+    const int have = fs_topk_warp(s_kd, s_id, n, k, s_hist, s_ckd, s_cid, [&](int rank, uint32_t kd, long long id) { pk[rank] = kd; pi[rank] = id; });
+    for (int i = have + (int)threadIdx.x; i < k; i += 32) { pk[i] = KEY_SENTINEL_D; pi[i] = KEY_SENTINEL_ID; }
     __syncwarp();
     if (threadIdx.x == 0) {
       __threadfence();
@@ -136,23 +141,17 @@ static __global__ void __launch_bounds__(FS_THREADS) flat_small_kernel(const FsA
   const int tot = nslices * k;  // <= FS_PAIRS (launcher)
   const uint32_t* allk = a.part_kd + (size_t)qi * nslices * k;
   const long long* alli = a.part_id + (size_t)qi * nslices * k;
-  if (threadIdx.x == 0) s_n = 0;
-  __syncthreads();
-  for (int j = threadIdx.x; j < tot; j += FS_THREADS) {
-    const uint32_t kd = __ldcg(allk + j);
-    const long long id = __ldcg(alli + j);
-    if (!(kd == KEY_SENTINEL_D && id == KEY_SENTINEL_ID)) { const int p = atomicAdd(&s_n, 1); s_kd[p] = kd; s_id[p] = id; }
-  }
+  for (int j = threadIdx.x; j < tot; j += FS_THREADS) { s_kd[j] = __ldcg(allk + j); s_id[j] = __ldcg(alli + j); }  // empty slots carry the sentinel pair
   __syncthreads();
   if (threadIdx.x < 32) {
-    const int n = s_n;
-    fs_topk_warp(s_kd, s_id, n, k, s_hist, s_ckd, s_cid, [&](int rank, uint32_t kd, long long id) {
+    const int n = tot;
+    const int have = fs_topk_warp(s_kd, s_id, n, k, s_hist, s_ckd, s_cid, [&](int rank, uint32_t kd, long long id) {
       const float v = ord2f(kd);
       const float raw = L2 ? v : -v;
       a.out_dist[(size_t)qi * k + rank] = L2 ? raw : __fsub_rn(1.0f, raw);
       a.out_ids[(size_t)qi * k + rank] = id;
     });
-    for (int i = min(n, k) + (int)threadIdx.x; i < k; i += 32) { a.out_dist[(size_t)qi * k + i] = 0.f; a.out_ids[(size_t)qi * k + i] = -1; }
+    for (int i = have + (int)threadIdx.x; i < k; i += 32) { a.out_dist[(size_t)qi * k + i] = 0.f; a.out_ids[(size_t)qi * k + i] = -1; }
   }
 }
 

@@ -19,7 +19,10 @@
 #include <algorithm>
 #include <cmath>
 #include <queue>
+#include <memory>
+#include <mutex>
 #include <random>
+#include <thread>
 
 #include "index.h"
 #include "scan_kernels.cuh"
@@ -84,11 +87,23 @@ struct HostGraph {
   std::vector<uint32_t> visited;
   uint32_t tag = 0;
   int64_t ndeleted = 0;
+  // concurrent insertion (hnswlib's locking scheme): one lock per node for its link lists, one for the entry point /
+  // max level, one for slot allocation + label map + level generator; every worker owns a visited-tag array
+  struct VisitCtx { std::vector<uint32_t> visited; uint32_t tag = 0; };
+  std::unique_ptr<std::mutex[]> node_mu;
+  int64_t node_mu_cap = 0;
+  struct Locks { std::mutex global_mu, alloc_mu; };
+  std::unique_ptr<Locks> lk{new Locks()};  // (heap-held so that the graph object stays movable)
 
   void init(int metric_, int d_, int M_, int efc_, int64_t seed) {
     metric = metric_; d = d_; M = M_; maxM = M_; maxM0 = 2 * (size_t)M_; efc = std::max((size_t)efc_, (size_t)M_);
     mult = 1 / log(1.0 * M_);
     rng.seed((unsigned)seed);
+  }
+  void reserve_locks(int64_t ncap) {
+    if (ncap <= node_mu_cap) return;
+    node_mu.reset(new std::mutex[(size_t)ncap]);
+    node_mu_cap = ncap;
   }
   void reserve(int64_t ncap) {  // resizeIndex
     if (ncap <= cap) return;
@@ -103,7 +118,10 @@ struct HostGraph {
   }
   tableint* ll(tableint i, int level) { return level == 0 ? &link0[(size_t)i * (maxM0 + 1)] : &linkup[i][(size_t)(level - 1) * (maxM + 1)]; }
 
-  HHeap search_layer(tableint ep, const float* q, int layer) {
+  template <bool MT>
+  HHeap search_layer(tableint ep, const float* q, int layer, VisitCtx* vc = nullptr) {
+    std::vector<uint32_t>& visited = MT ? vc->visited : this->visited;
+    uint32_t& tag = MT ? vc->tag : this->tag;
     if (++tag == 0) { std::fill(visited.begin(), visited.end(), 0u); tag = 1; }
     HHeap top, cand;
     float lower;
@@ -114,6 +132,8 @@ struct HostGraph {
       HPair cur = cand.top();
       if ((-cur.first) > lower && top.size() == efc) break;
       cand.pop();
+      std::unique_lock<std::mutex> nl;
+      if (MT) nl = std::unique_lock<std::mutex>(node_mu[cur.second]);
       const tableint* l = ll(cur.second, layer);
       const size_t size = l[0];
       for (size_t j = 1; j <= size; ++j) {
@@ -147,6 +167,7 @@ struct HostGraph {
     }
     for (const HPair& p : ret) top.emplace(-p.first, p.second);
   }
+  template <bool MT>
   tableint connect(tableint cur_c, HHeap& top, int level) {
     const size_t mcur = level ? maxM : maxM0;
     heuristic(top, M);
@@ -157,6 +178,8 @@ struct HostGraph {
     l[0] = (tableint)sel.size();
     for (size_t i = 0; i < sel.size(); ++i) l[1 + i] = sel[i];
     for (size_t idx = 0; idx < sel.size(); ++idx) {
+      std::unique_lock<std::mutex> nl;
+      if (MT) nl = std::unique_lock<std::mutex>(node_mu[sel[idx]]);
       tableint* lo = ll(sel[idx], level);
       const size_t sz = lo[0];
       if (sz < mcur) { lo[1 + sz] = cur_c; lo[0] = (tableint)(sz + 1); }
@@ -172,16 +195,30 @@ struct HostGraph {
     }
     return next_ep;
   }
-  // addPoint for a NEW label (replacing an existing label = mark the old node deleted, then insert)
-  void add_point(const float* x, int64_t label) {
-    auto it = lookup.find(label);
-    if (it != lookup.end()) { if (!deleted[it->second]) { deleted[it->second] = 1; ++ndeleted; } lookup.erase(it); }
-    if (n >= cap) reserve(std::max<int64_t>(1024, cap * 2));
-    const tableint cur_c = (tableint)n++;
-    lookup[label] = cur_c;
-    std::uniform_real_distribution<double> U(0.0, 1.0);
-    const int curlevel = (int)(-log(U(rng)) * mult);
+  // addPoint for a NEW label (replacing an existing label = mark the old node deleted, then insert).  MT = several threads
+  // insert at once (the reference's ParallelFor over addPoint, vector_index_hnsw.cc:229-243); capacity and locks are
+  // reserved by the caller, so no container is re-allocated while workers run.
+  template <bool MT>
+  void add_point(const float* x, int64_t label, VisitCtx* vc = nullptr) {
+    tableint cur_c;
+    int curlevel;
+    {
+      std::unique_lock<std::mutex> al;
+      if (MT) al = std::unique_lock<std::mutex>(lk->alloc_mu);
+      auto it = lookup.find(label);
+      if (it != lookup.end()) { if (!deleted[it->second]) { deleted[it->second] = 1; ++ndeleted; } lookup.erase(it); }
+      if (!MT && n >= cap) reserve(std::max<int64_t>(1024, cap * 2));
+      cur_c = (tableint)n++;
+      lookup[label] = cur_c;
+      std::uniform_real_distribution<double> U(0.0, 1.0);
+      curlevel = (int)(-log(U(rng)) * mult);
+    }
+    std::unique_lock<std::mutex> own;
+    if (MT) own = std::unique_lock<std::mutex>(node_mu[cur_c]);
+    std::unique_lock<std::mutex> gl;
+    if (MT) gl = std::unique_lock<std::mutex>(lk->global_mu);
     const int maxlevelcopy = maxlevel;
+    if (MT && curlevel <= maxlevelcopy) gl.unlock();
     tableint cur = enterpoint;
     memcpy(&data[(size_t)cur_c * d], x, sizeof(float) * d);
     labels[cur_c] = label; levels[cur_c] = curlevel; deleted[cur_c] = 0;
@@ -195,6 +232,8 @@ struct HostGraph {
           bool changed = true;
           while (changed) {
             changed = false;
+            std::unique_lock<std::mutex> nl;
+            if (MT) nl = std::unique_lock<std::mutex>(node_mu[cur]);
             const tableint* l = ll(cur, level);
             const int size = l[0];
             for (int i = 1; i <= size; ++i) {
@@ -205,8 +244,8 @@ struct HostGraph {
         }
       }
       for (int level = std::min(curlevel, maxlevelcopy); level >= 0; --level) {
-        HHeap top = search_layer(cur, q, level);
-        cur = connect(cur_c, top, level);
+        HHeap top = search_layer<MT>(cur, q, level, vc);
+        cur = connect<MT>(cur_c, top, level);
       }
     } else { enterpoint = 0; maxlevel = curlevel; }
     if (curlevel > maxlevelcopy) { enterpoint = cur_c; maxlevel = curlevel; }
@@ -227,104 +266,122 @@ struct HnswDev {
   int has_deletions;
 };
 
-constexpr int HNSW_WARPS = 4;
+constexpr int HNSW_THREADS = 128;   // one CTA per query: warp 0 walks the graph, all 32 quads score a hop's neighbours together
+constexpr int HNSW_CAND_SMEM = 1024; // candidate-heap entries kept in shared memory (the levels near the root); deeper ones spill to global
 
 struct HeapEnt { float d; unsigned int id; };
 
-// binary heaps operated by one lane.  cmp_max = true: largest distance on top.
+// Binary heap operated by ONE lane.  MAXH: largest distance on top.  Entries [0, nsm) live in shared memory, the rest in
+// global memory: a sift walks a root-to-leaf path, whose upper levels (the hot ones) are the shared part.
+struct HeapRef {
+  HeapEnt* sm;
+  HeapEnt* gl;
+  int nsm;
+  __device__ __forceinline__ HeapEnt get(int i) const { return i < nsm ? sm[i] : gl[i]; }
+  __device__ __forceinline__ void set(int i, HeapEnt e) const { if (i < nsm) sm[i] = e; else gl[i] = e; }
+};
 template <bool MAXH>
 __device__ __forceinline__ bool h_before(float a, float b) { return MAXH ? a > b : a < b; }
 template <bool MAXH>
-__device__ void h_push(HeapEnt* h, int& n, float d, unsigned int id) {
+__device__ void h_push(const HeapRef& h, int& n, float d, unsigned int id) {
   int i = n++;
   while (i > 0) {
     const int p = (i - 1) >> 1;
-    if (h_before<MAXH>(d, h[p].d)) { h[i] = h[p]; i = p; } else break;
+    const HeapEnt pe = h.get(p);
+    if (h_before<MAXH>(d, pe.d)) { h.set(i, pe); i = p; } else break;
   }
-  h[i].d = d; h[i].id = id;
+  HeapEnt e; e.d = d; e.id = id;
+  h.set(i, e);
 }
 template <bool MAXH>
-__device__ void h_pop(HeapEnt* h, int& n) {
-  const HeapEnt last = h[--n];
+__device__ void h_pop(const HeapRef& h, int& n) {
+  const HeapEnt last = h.get(--n);
   int i = 0;
   for (;;) {
     int c = 2 * i + 1;
     if (c >= n) break;
-    if (c + 1 < n && h_before<MAXH>(h[c + 1].d, h[c].d)) ++c;
-    if (h_before<MAXH>(h[c].d, last.d)) { h[i] = h[c]; i = c; } else break;
+    HeapEnt ce = h.get(c);
+    if (c + 1 < n) { const HeapEnt c2 = h.get(c + 1); if (h_before<MAXH>(c2.d, ce.d)) { ce = c2; ++c; } }
+    if (h_before<MAXH>(ce.d, last.d)) { h.set(i, ce); i = c; } else break;
   }
-  if (n > 0) h[i] = last;
+  if (n > 0) h.set(i, last);
 }
 
+// One CTA (128 threads) per query.  Warp 0 runs hnswlib's control flow (greedy descent of the upper layers, then
+// searchBaseLayerST): it pops the closest candidate, reads its link list 32 neighbours at a time, keeps the unvisited ones in
+// list order; then ALL 32 quads of the CTA compute those rows' distances in one round (exact AVX-512 order, so the traversal
+// is the CPU traversal); lane 0 applies the heap updates in neighbour order.  Two block barriers per batch of <= 32 neighbours.
 template <bool L2>
-__global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(const HnswDev g, const float* __restrict__ queries, long long nq,
-                                                                     int k, int ef, FilterDev filt, unsigned int* visited /*[nq, words]*/,
-                                                                     long long words, HeapEnt* cand_pool, int cand_cap, float* out_dist,
-                                                                     long long* out_ids, int* err_flag) {
+__global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_kernel(const HnswDev g, const float* __restrict__ queries, long long nq,
+                                                                  int k, int ef, FilterDev filt, unsigned int* visited /*[nq, words]*/,
+                                                                  long long words, HeapEnt* cand_pool, int cand_cap, float* out_dist,
+                                                                  long long* out_ids, int* err_flag) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long qi = (long long)blockIdx.x * HNSW_WARPS + wib;
+  __shared__ float s_d[32];
+  __shared__ unsigned int s_id[32];
+  __shared__ int s_m;  // rows to score this round; -1 = the walk is over
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long qi = blockIdx.x;
   const int d = g.d;
   const size_t qbytes = ((size_t)d * 4 + 15) / 16 * 16;
-  const size_t per_warp = qbytes + (size_t)(ef + 1) * sizeof(HeapEnt) + 64 * 4;
-  unsigned char* base = smem + (size_t)wib * ((per_warp + 15) / 16 * 16);
-  float* qs = reinterpret_cast<float*>(base);
-  HeapEnt* top = reinterpret_cast<HeapEnt*>(base + qbytes);
-  float* s_d = reinterpret_cast<float*>(base + qbytes + (size_t)(ef + 1) * sizeof(HeapEnt));  // [32]
-  unsigned int* s_id = reinterpret_cast<unsigned int*>(s_d + 32);                              // [32]
-  if (qi >= nq) return;  // whole warp
-  for (int i = lane; i < d; i += 32) qs[i] = queries[(size_t)qi * d + i];
-  __syncwarp();
+  float* qs = reinterpret_cast<float*>(smem);
+  HeapEnt* top_sm = reinterpret_cast<HeapEnt*>(smem + qbytes);                                   // [ef + 1]
+  HeapEnt* cand_sm = reinterpret_cast<HeapEnt*>(smem + qbytes + (size_t)(ef + 1) * sizeof(HeapEnt));  // [HNSW_CAND_SMEM]
+  for (int i = threadIdx.x; i < d; i += HNSW_THREADS) qs[i] = queries[(size_t)qi * d + i];
+  if (g.n == 0) {
+    for (int i = threadIdx.x; i < k; i += HNSW_THREADS) { out_dist[(size_t)qi * k + i] = 0.f; out_ids[(size_t)qi * k + i] = -1; }
+    return;
+  }
+  __syncthreads();
   const bool vec = (d & 3) == 0;
-  const int quad = lane >> 2, t = lane & 3;
+  const int quad = threadIdx.x >> 2, t = threadIdx.x & 3;
   unsigned int* vis = visited + (size_t)qi * words;
-  HeapEnt* cand = cand_pool + (size_t)qi * cand_cap;
+  const HeapRef top{top_sm, top_sm, ef + 1};
+  const HeapRef cand{cand_sm, cand_pool + (size_t)qi * cand_cap, HNSW_CAND_SMEM};
   const bool filtered = filt.has_range || filt.sorted_ids != nullptr;
   const bool strict_stop = filtered || g.has_deletions;
 
-  // distances of s_id[0..m) -> s_d[0..m), 8 rows per round
-  auto batch_dist = [&](int m) {
-    for (int b = 0; b < m; b += 8) {
-      const int i = b + quad;
-      const unsigned int row = s_id[i < m ? i : 0];
-      float v = quad_distance<L2>(g.data + (size_t)row * d, qs, d, t, vec);
-      if (!L2) v = __fsub_rn(1.0f, v);  // hnswlib InnerProductDistance
-      if (i < m && t == 0) s_d[i] = v;
-    }
-    __syncwarp();
+  // distances of s_id[0..m) -> s_d[0..m): one row per quad, every thread of the CTA calls (m <= 32)
+  auto score = [&](int m) {
+    const unsigned int row = s_id[quad < m ? quad : 0];
+    float v = quad_distance<L2>(g.data + (size_t)row * d, qs, d, t, vec);
+    if (!L2) v = __fsub_rn(1.0f, v);  // hnswlib InnerProductDistance
+    if (quad < m && t == 0) s_d[quad] = v;
   };
 
-  if (g.n == 0) {
-    for (int i = lane; i < k; i += 32) { out_dist[(size_t)qi * k + i] = 0.f; out_ids[(size_t)qi * k + i] = -1; }
-    return;
-  }
+  // ---- entry point ----
   unsigned int cur = g.enterpoint;
-  if (lane == 0) s_id[0] = cur;
-  __syncwarp();
-  batch_dist(1);
+  if (threadIdx.x == 0) s_id[0] = cur;
+  __syncthreads();
+  score(1);
+  __syncthreads();
   float curdist = s_d[0];
-  // ---- upper layers: greedy descent ----
+  // ---- upper layers: greedy descent (every thread tracks the same state) ----
   for (int level = g.maxlevel; level > 0; --level) {
     bool changed = true;
     while (changed) {
       changed = false;
       const unsigned int* l = g.linkup + g.up_off[cur] + (size_t)(level - 1) * (g.maxM + 1);
       const int size = (int)l[0];
-      __syncwarp();
-      if (lane < size) s_id[lane] = l[1 + lane];
-      __syncwarp();
-      batch_dist(size);
-      for (int i = 0; i < size; ++i) {  // uniform across the warp: every lane tracks the same state
-        const float dd = s_d[i];
-        if (dd < curdist) { curdist = dd; cur = s_id[i]; changed = true; }
+      for (int c0 = 0; c0 < size; c0 += 32) {
+        const int m = min(32, size - c0);
+        __syncthreads();  // previous round's s_d / s_id fully consumed
+        if (warp == 0 && lane < m) s_id[lane] = l[1 + c0 + lane];
+        __syncthreads();
+        score(m);
+        __syncthreads();
+        for (int i = 0; i < m; ++i) {
+          const float dd = s_d[i];
+          if (dd < curdist) { curdist = dd; cur = s_id[i]; changed = true; }
+        }
       }
-      __syncwarp();
     }
   }
   // ---- base layer: searchBaseLayerST ----
   int ntop = 0, ncand = 0;
-  float lower;
-  {
+  float lower = 3.402823466e+38f;
+  bool overflow = false;
+  if (warp == 0) {
     const long long lab = g.labels[cur];
     const bool ok = !g.deleted[cur] && filter_pass(filt, lab);
     if (lane == 0) {
@@ -334,74 +391,84 @@ __global__ void __launch_bounds__(HNSW_WARPS * 32) hnsw_search_kernel(const Hnsw
     }
     lower = ok ? curdist : 3.402823466e+38f;
   }
-  __syncwarp();
-  bool overflow = false;
+  // warp 0 state that survives across rounds: the node being expanded and how far into its link list we are
+  unsigned int node = 0;
+  int size = 0, c0 = 0;
+  bool expanding = false;
   for (;;) {
-    // lane 0 owns the heaps; broadcast the decision
-    int go = 0;
-    unsigned int node = 0;
-    if (lane == 0) {
-      if (ncand > 0) {
-        const float cd = cand[0].d;
-        const bool stop = cd > lower && (ntop == ef || !strict_stop);
-        if (!stop) { node = cand[0].id; h_pop<false>(cand, ncand); go = 1; }
+    __syncthreads();  // (A) s_d / s_id of the previous round consumed by everyone
+    if (warp == 0) {
+      int m = -1;
+      for (;;) {  // find the next non-empty batch of unvisited neighbours
+        if (!expanding) {
+          int go = 0;
+          if (lane == 0 && ncand > 0) {
+            const HeapEnt ce = cand.get(0);
+            const bool stop = ce.d > lower && (ntop == ef || !strict_stop);
+            if (!stop) { node = ce.id; h_pop<false>(cand, ncand); go = 1; }
+          }
+          go = __shfl_sync(0xffffffffu, go, 0);
+          if (!go || overflow) { m = -1; break; }
+          node = __shfl_sync(0xffffffffu, node, 0);
+          size = (int)g.link0[(size_t)node * (g.maxM0 + 1)];
+          c0 = 0;
+          expanding = true;
+        }
+        if (c0 >= size) { expanding = false; continue; }
+        const unsigned int* l = g.link0 + (size_t)node * (g.maxM0 + 1) + 1 + c0;
+        const int cnt = min(32, size - c0);
+        c0 += 32;
+        unsigned int nb = 0;
+        bool fresh = false;
+        if (lane < cnt) { nb = l[lane]; fresh = ((vis[nb >> 5] >> (nb & 31)) & 1u) == 0u; }
+        const unsigned int mask = __ballot_sync(0xffffffffu, fresh);
+        if (fresh) {
+          atomicOr(&vis[nb >> 5], 1u << (nb & 31));
+          s_id[__popc(mask & ((1u << lane) - 1u))] = nb;
+        }
+        m = __popc(mask);
+        if (m > 0) break;
       }
+      if (lane == 0) s_m = m;
     }
-    go = __shfl_sync(0xffffffffu, go, 0);
-    if (!go) break;
-    node = __shfl_sync(0xffffffffu, node, 0);
-    const unsigned int* l = g.link0 + (size_t)node * (g.maxM0 + 1);
-    const int size = (int)l[0];
-    // unvisited neighbours, in list order
-    unsigned int nb = 0;
-    bool fresh = false;
-    if (lane < size) {
-      nb = l[1 + lane];
-      fresh = ((vis[nb >> 5] >> (nb & 31)) & 1u) == 0u;
-    }
-    const unsigned int mask = __ballot_sync(0xffffffffu, fresh);
-    const int m = __popc(mask);
-    if (fresh) {
-      atomicOr(&vis[nb >> 5], 1u << (nb & 31));
-      s_id[__popc(mask & ((1u << lane) - 1u))] = nb;
-    }
-    __syncwarp();
-    if (m == 0) continue;
-    batch_dist(m);
-    // admissibility of each fresh neighbour (labels + filter), evaluated in parallel
-    bool allowed = false;
-    if (lane < m) { const unsigned int c = s_id[lane]; allowed = !g.deleted[c] && filter_pass(filt, g.labels[c]); }
-    const unsigned int amask = __ballot_sync(0xffffffffu, allowed);
-    if (lane == 0) {
-      for (int i = 0; i < m; ++i) {
-        const float dd = s_d[i];
-        if (ntop < ef || lower > dd) {
-          if (ncand >= cand_cap) { overflow = true; break; }
-          h_push<false>(cand, ncand, dd, s_id[i]);
-          if ((amask >> i) & 1u) h_push<true>(top, ntop, dd, s_id[i]);
-          if (ntop > ef) h_pop<true>(top, ntop);
-          if (ntop > 0) lower = top[0].d;
+    __syncthreads();  // (B) s_id / s_m published
+    const int m = s_m;
+    if (m < 0) break;
+    score(m);
+    __syncthreads();  // (C) s_d complete
+    if (warp == 0) {
+      bool allowed = false;
+      if (lane < m) { const unsigned int c = s_id[lane]; allowed = !g.deleted[c] && filter_pass(filt, g.labels[c]); }
+      const unsigned int amask = __ballot_sync(0xffffffffu, allowed);
+      if (lane == 0) {
+        for (int i = 0; i < m; ++i) {
+          const float dd = s_d[i];
+          if (ntop < ef || lower > dd) {
+            if (ncand >= cand_cap) { overflow = true; break; }
+            h_push<false>(cand, ncand, dd, s_id[i]);
+            if ((amask >> i) & 1u) h_push<true>(top, ntop, dd, s_id[i]);
+            if (ntop > ef) h_pop<true>(top, ntop);
+            if (ntop > 0) lower = top.get(0).d;
+          }
         }
       }
+      lower = __shfl_sync(0xffffffffu, lower, 0);
+      overflow = __shfl_sync(0xffffffffu, (int)overflow, 0) != 0;
     }
-    lower = __shfl_sync(0xffffffffu, lower, 0);
-    overflow = __shfl_sync(0xffffffffu, (int)overflow, 0) != 0;
-    if (overflow) break;
   }
-  if (overflow && lane == 0) atomicExch(err_flag, 1);
-  // keep the k best, emit ascending by (distance, label)
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
+    if (overflow) atomicExch(err_flag, 1);
+    // keep the k best, emit ascending by (distance, label)
     while (ntop > k) h_pop<true>(top, ntop);
-    // selection sort on (d, label) of <= k entries, ascending
-    for (int i = 0; i < ntop; ++i) {
+    for (int i = 0; i < ntop; ++i) {  // selection sort of <= k entries
       int best = i;
       for (int j = i + 1; j < ntop; ++j) {
-        const long long lj = g.labels[top[j].id], lb = g.labels[top[best].id];
-        if (top[j].d < top[best].d || (top[j].d == top[best].d && lj < lb)) best = j;
+        const long long lj = g.labels[top_sm[j].id], lb = g.labels[top_sm[best].id];
+        if (top_sm[j].d < top_sm[best].d || (top_sm[j].d == top_sm[best].d && lj < lb)) best = j;
       }
-      const HeapEnt tmp = top[i]; top[i] = top[best]; top[best] = tmp;
-      out_dist[(size_t)qi * k + i] = top[i].d;
-      out_ids[(size_t)qi * k + i] = g.labels[top[i].id];
+      const HeapEnt tmp = top_sm[i]; top_sm[i] = top_sm[best]; top_sm[best] = tmp;
+      out_dist[(size_t)qi * k + i] = top_sm[i].d;
+      out_ids[(size_t)qi * k + i] = g.labels[top_sm[i].id];
     }
     for (int i = ntop; i < k; ++i) { out_dist[(size_t)qi * k + i] = 0.f; out_ids[(size_t)qi * k + i] = -1; }
   }
@@ -466,19 +533,49 @@ struct HnswIndex : IndexBase {
   void add(int64_t n, const float* x, const int64_t* in_ids, bool) override {
     std::unique_lock<std::shared_mutex> wl(rw);
     if (G.n + n > max_element_limit) fail(B200VS_EINTERNAL, "upsert failed, exceeds max elements");
-    std::vector<float> tmp(dim);
-    for (int64_t i = 0; i < n; ++i) {
+    auto prepared = [&](int64_t i, std::vector<float>& tmp) -> const float* {
       const float* xi = x + (size_t)i * dim;
-      if (metric == B200VS_COSINE) {  // NormalizeVectorForHnsw, vector_index_utils.cc:493-500
-        float norm = 0.0f;
-        for (int j = 0; j < dim; ++j) norm += xi[j] * xi[j];
-        norm = 1.0f / (sqrtf(norm) + 1e-30f);
-        for (int j = 0; j < dim; ++j) tmp[j] = xi[j] * norm;
-        xi = tmp.data();
-      }
-      G.add_point(xi, in_ids[i]);
+      if (metric != B200VS_COSINE) return xi;
+      float norm = 0.0f;  // NormalizeVectorForHnsw, vector_index_utils.cc:493-500
+      for (int j = 0; j < dim; ++j) norm += xi[j] * xi[j];
+      norm = 1.0f / (sqrtf(norm) + 1e-30f);
+      for (int j = 0; j < dim; ++j) tmp[j] = xi[j] * norm;
+      return tmp.data();
+    };
+    const int nthreads = (int)std::min<int64_t>(std::max(1, params.hnsw_build_threads), n);
+    if (nthreads <= 1) {  // single writer: deterministic graph (equal to the oracle's for the same insertion order)
+      std::vector<float> tmp(dim);
+      for (int64_t i = 0; i < n; ++i) G.add_point<false>(prepared(i, tmp), in_ids[i]);
+    } else {  // concurrent insertion, as the reference's thread pool does (hnsw.cc:229-243)
+      G.reserve(std::max<int64_t>(G.cap, G.n + n));
+      G.reserve_locks(G.cap);
+      std::atomic<int64_t> next{0};
+      if (G.n == 0) { std::vector<float> tmp(dim); G.add_point<false>(prepared(0, tmp), in_ids[0]); next = 1; }  // hnswlib: first element alone
+      std::vector<std::thread> ts;
+      for (int t = 0; t < nthreads; ++t)
+        ts.emplace_back([&]() {
+          HostGraph::VisitCtx vc;
+          vc.visited.assign((size_t)G.cap, 0u);
+          std::vector<float> tmp(dim);
+          for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= n) break;
+            G.add_point<true>(prepared(i, tmp), in_ids[i], &vc);
+          }
+        });
+      for (auto& th : ts) th.join();
     }
     dirty = true;
+  }
+  // hnswlib getDataByLabel (hnsw.cc:383-395): the stored (for cosine: normalised) vector of a live label
+  void reconstruct(int64_t n, const int64_t* in_ids, float* out, uint8_t* found) override {
+    std::shared_lock<std::shared_mutex> rl(rw);
+    for (int64_t i = 0; i < n; ++i) {
+      auto it = G.lookup.find(in_ids[i]);
+      const bool ok = it != G.lookup.end() && !G.deleted[it->second];
+      if (found) found[i] = ok ? 1 : 0;
+      if (ok) memcpy(out + (size_t)i * dim, G.vec(it->second), (size_t)dim * 4);
+    }
   }
   // markDelete, hnsw.cc:256-281
   int64_t remove(int64_t n, const int64_t* del) override {
@@ -532,10 +629,9 @@ struct HnswIndex : IndexBase {
     g.data = d_data.p; g.labels = d_labels.p; g.link0 = d_link0.p; g.up_off = d_upoff.p; g.linkup = d_linkup.p; g.deleted = d_deleted.p;
     g.n = G.n; g.d = dim; g.maxM = (int)G.maxM; g.maxM0 = (int)G.maxM0; g.maxlevel = G.maxlevel; g.l2 = metric == B200VS_L2;
     g.enterpoint = G.enterpoint; g.has_deletions = G.ndeleted > 0;
-    if (G.maxM0 > 32) fail(B200VS_EVECTOR_NOT_SUPPORT, "nlinks > 16 is not supported by the GPU search kernel");
     const long long words = (G.n + 31) / 32;
     unsigned int* visited = scratch.alloc<unsigned int>((size_t)nq * words);
-    const int cand_cap = (int)std::min<int64_t>(G.n + 1, 65536);
+    const int cand_cap = (int)std::max<int64_t>(HNSW_CAND_SMEM, std::min<int64_t>(G.n + 1, 65536));
     HeapEnt* cand = scratch.alloc<HeapEnt>((size_t)nq * cand_cap);
     int* err = scratch.alloc<int>(1);
     B200VS_CUDA(cudaMemsetAsync(visited, 0, (size_t)nq * words * 4, s));
@@ -543,17 +639,16 @@ struct HnswIndex : IndexBase {
     FilterDev f;
     f.has_range = sc.has_range; f.negate = sc.negate; f.rmin = sc.rmin; f.rmax = sc.rmax; f.sorted_ids = sc.sorted_ids_dev; f.n_ids = sc.n_ids;
     const size_t qbytes = ((size_t)dim * 4 + 15) / 16 * 16;
-    const size_t per_warp = (qbytes + (size_t)(ef_run + 1) * sizeof(HeapEnt) + 64 * 4 + 15) / 16 * 16;
-    const size_t smem = per_warp * HNSW_WARPS;
-    if (smem > 227 * 1024) fail(B200VS_EILLEGAL_PARAMETERS, "efsearch / dimension too large for the search kernel");
-    const unsigned grid = (unsigned)cdiv(nq, HNSW_WARPS);
+    const size_t smem = qbytes + (size_t)(ef_run + 1) * sizeof(HeapEnt) + (size_t)HNSW_CAND_SMEM * sizeof(HeapEnt);
+    if (smem > 200 * 1024) fail(B200VS_EILLEGAL_PARAMETERS, "efsearch / dimension too large for the search kernel");
+    const unsigned grid = (unsigned)nq;
     ScopedKernelTimer timer(this, s, profiling);
     if (g.l2) {
-      B200VS_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      hnsw_search_kernel<true><<<grid, HNSW_WARPS * 32, smem, s>>>(g, q, nq, k, ef_run, f, visited, words, cand, cand_cap, od, oi, err);
+      B200VS_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      hnsw_search_kernel<true><<<grid, HNSW_THREADS, smem, s>>>(g, q, nq, k, ef_run, f, visited, words, cand, cand_cap, od, oi, err);
     } else {
-      B200VS_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      hnsw_search_kernel<false><<<grid, HNSW_WARPS * 32, smem, s>>>(g, q, nq, k, ef_run, f, visited, words, cand, cand_cap, od, oi, err);
+      B200VS_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      hnsw_search_kernel<false><<<grid, HNSW_THREADS, smem, s>>>(g, q, nq, k, ef_run, f, visited, words, cand, cand_cap, od, oi, err);
     }
     timer.stop();
     B200VS_CUDA(cudaGetLastError());

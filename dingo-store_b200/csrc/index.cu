@@ -355,6 +355,18 @@ struct FlatIndex : IndexBase {
     run_scan(this, j, nq, q, max_results, od, nullptr, oi, oc, s);
   }
 
+  void reconstruct(int64_t n, const int64_t* in_ids, float* out, uint8_t* found) override {
+    std::shared_lock<std::shared_mutex> rl(rw);
+    std::lock_guard<std::mutex> gl(gpu_mu);
+    set_device();
+    for (int64_t i = 0; i < n; ++i) {
+      auto it = id2row.find(in_ids[i]);
+      if (found) found[i] = it != id2row.end() ? 1 : 0;
+      if (it != id2row.end())
+        B200VS_CUDA(cudaMemcpyAsync(out + (size_t)i * dim, vecs.p + (size_t)it->second * dim, (size_t)dim * 4, cudaMemcpyDeviceToHost, stream));
+    }
+    B200VS_CUDA(cudaStreamSynchronize(stream));
+  }
   int64_t count() const override { return rows - ndeleted; }
   int64_t deleted_count() const override { return ndeleted; }
   int64_t memory_size() const override { return (int64_t)(vecs.cap * 4 + ids.cap * 8 + norms.cap * 4); }

@@ -263,6 +263,11 @@ struct IndexBase {
   }
   virtual int resolve_nprobe_api(const SearchCtx& sc) const { (void)sc; return 1; }
 
+  virtual void reconstruct(int64_t n, const int64_t* ids, float* out, uint8_t* found) {
+    (void)n; (void)ids; (void)out; (void)found;
+    fail(B200VS_EVECTOR_NOT_SUPPORT, "reconstruct is implemented for HNSW and FLAT");
+  }
+  virtual int sub_type() const { return (int)type; }
   virtual int64_t count() const = 0;
   virtual int64_t deleted_count() const { return 0; }
   virtual int64_t memory_size() const = 0;

@@ -122,6 +122,8 @@ struct PqScanArgs {
   const float* sim;  // [nq, M*256]
   const float* pre;  // [nlist, M*256] (L2) or null
   int M, nprobe, k, nsplit, pool_cap;
+  int has_thr;       // range search: fixed initial threshold (strict), k = max results kept
+  uint32_t thr_key;
   uint32_t* ws_kd;
   long long* ws_kid;
   FilterDev filt;
@@ -136,6 +138,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) pq_scan_select_kernel(const PqSc
   const int qi = blockIdx.y, split = blockIdx.x;
   BlockSelect sel;
   sel.init(smem + (size_t)T * 4, a.pool_cap, a.k);
+  if (a.has_thr && threadIdx.x == 0) { *sel.thr_d = a.thr_key; *sel.thr_id = (long long)0x8000000000000000LL; }
+  __syncthreads();
   const float* simq = a.sim + (size_t)qi * T;
   if (!L2) {
     for (int i = threadIdx.x; i < T; i += blockDim.x) tab[i] = simq[i];
@@ -209,6 +213,7 @@ struct IvfPqIndex : IndexBase {
     if (d % M != 0) fail(B200VS_EILLEGAL_PARAMETERS, "dimension must be divisible by nsubvector");
   }
   bool is_trained() const override { return mode != kNone; }
+  int sub_type() const override { return mode == kFlat ? (int)B200VS_FLAT : mode == kIvfPq ? (int)B200VS_IVF_PQ : -1; }  // ivf_pq.cc:474
 
   void install(const float* h_cent, const float* h_cb) {
     quiesce();
@@ -432,13 +437,17 @@ struct IvfPqIndex : IndexBase {
     if (mode == kFlat) {  // delegate to the inner Flat index, sharing this call's stream and scratch discipline
       std::shared_lock<std::shared_mutex> rl(flat->rw);
       LaneGuard lg(flat.get(), s);
-      SearchCtx sc2 = sc;
-      if (sc.sorted_ids_dev) {  // the filter list lives in the outer lane's scratch: still valid (same stream, still locked)
-      }
-      flat->search_dev(nq, xq, k, sc2, od, oi, s);
+      flat->search_dev(nq, xq, k, sc, od, oi, s);  // (an id-list filter lives in the outer lane's scratch: same stream, still locked)
       for (int i = 0; i < 8; ++i) stats[i] = flat->stats[i];
       return;
     }
+    scan_codes(nq, xq, k, sc, false, 0.f, od, oi, nullptr, s);
+  }
+
+  // coarse quantiser -> per-query LUT -> code scan + select -> merge.  Range mode (has_thr): keep hits strictly inside the
+  // raw threshold (L2: dis < thr; IP: dis > thr), at most k of them, closest first; out_counts = hits per query.
+  void scan_codes(int64_t nq, const float* xq, int k, const SearchCtx& sc, bool has_thr, float thr_raw, float* od, long long* oi, int* oc,
+                  cudaStream_t s) {
     const float* q = prepare_queries(nq, xq, s);
     const bool l2 = metric == B200VS_L2;
     int nprobe = sc.nprobe > 0 ? sc.nprobe : 80;  // Constant::kSearchIvfPqParamNprobe, raw_ivf_pq.cc:170
@@ -458,12 +467,14 @@ struct IvfPqIndex : IndexBase {
     a.sim = sim; a.pre = l2 ? pre.p : nullptr; a.M = M; a.nprobe = nprobe; a.k = k;
     a.nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(nprobe, (148 * 2 + nq - 1) / nq));
     a.pool_cap = select_pool_cap(k, SCAN_THREADS);
+    a.has_thr = has_thr ? 1 : 0;
+    a.thr_key = has_thr ? f2ord(l2 ? thr_raw : -thr_raw) : 0;
     a.ws_kd = scratch.alloc<uint32_t>((size_t)nq * a.nsplit * k);
     a.ws_kid = scratch.alloc<long long>((size_t)nq * a.nsplit * k);
     a.filt.has_range = sc.has_range; a.filt.negate = sc.negate; a.filt.rmin = sc.rmin; a.filt.rmax = sc.rmax;
     a.filt.sorted_ids = sc.sorted_ids_dev; a.filt.n_ids = sc.n_ids;
     const size_t smem = (size_t)T * 4 + BlockSelect::smem_bytes(a.pool_cap);
-    if (smem > 227 * 1024) fail(B200VS_EILLEGAL_PARAMETERS, "nsubvector too large for the shared-memory LUT");
+    if (smem > 227 * 1024) fail(B200VS_EILLEGAL_PARAMETERS, "nsubvector / topk too large for the shared-memory LUT");
     const size_t smem2 = BlockSelect::smem_bytes(a.pool_cap);
     dim3 grid(a.nsplit, (unsigned)nq);
     ScopedKernelTimer timer(this, s, profiling);
@@ -472,27 +483,35 @@ struct IvfPqIndex : IndexBase {
       pq_scan_select_kernel<true><<<grid, SCAN_THREADS, smem, s>>>(a);
       timer.stop();
       B200VS_CUDA(cudaFuncSetAttribute(merge_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      merge_select_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, a.nsplit, k, a.pool_cap, od, nullptr, oi, nullptr, nullptr, nullptr);
+      merge_select_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, a.nsplit, k, a.pool_cap, od, nullptr, oi, oc, nullptr, nullptr);
     } else {
       B200VS_CUDA(cudaFuncSetAttribute(pq_scan_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       pq_scan_select_kernel<false><<<grid, SCAN_THREADS, smem, s>>>(a);
       timer.stop();
       B200VS_CUDA(cudaFuncSetAttribute(merge_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      merge_select_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, a.nsplit, k, a.pool_cap, od, nullptr, oi, nullptr, nullptr, nullptr);
+      merge_select_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, a.nsplit, k, a.pool_cap, od, nullptr, oi, oc, nullptr, nullptr);
     }
     B200VS_CUDA(cudaGetLastError());
     launch_count(3);
   }
 
+  // VectorIndexRawIvfPq::RangeSearch, vector_index_raw_ivf_pq.cc:212-278: faiss IndexIVFPQ::range_search on the codes —
+  // radius -> 1 - radius for IP / cosine (:229-232), L2 keeps dis < radius, IP keeps dis > radius; the same LUT scan with a
+  // threshold epilogue instead of the k-th-best threshold.  Untrained -> empty results (:219-222).
   void range_search_dev(int64_t nq, const float* xq, float radius, int max_results, const SearchCtx& sc, float* od, long long* oi,
                         int* oc, cudaStream_t s) override {
+    if (mode == kNone) {
+      fill_empty_results(nq, max_results, od, oi, s);
+      if (oc) B200VS_CUDA(cudaMemsetAsync(oc, 0, (size_t)nq * 4, s));
+      return;
+    }
     if (mode == kFlat) {
       std::shared_lock<std::shared_mutex> rl(flat->rw);
       LaneGuard lg(flat.get(), s);
       flat->range_search_dev(nq, xq, radius, max_results, sc, od, oi, oc, s);
       return;
     }
-    fail(B200VS_EVECTOR_NOT_SUPPORT, "range search on IVF-PQ codes is not implemented (SURVEY 8f-1)");
+    scan_codes(nq, xq, max_results, sc, true, ip_like() ? 1.0F - radius : radius, od, oi, oc, s);
   }
 
   int64_t count() const override { return mode == kFlat ? flat->count() : L.live; }

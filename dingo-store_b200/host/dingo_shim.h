@@ -207,6 +207,7 @@ class VectorIndex {
   virtual bool NeedToSave(int64_t last_save_log_behind) = 0;
   virtual bool SupportSave() { return false; }
   virtual uint32_t WriteOpParallelNum() { return 1; }
+  virtual pb::common::VectorIndexType VectorIndexSubType() { return pb::common::VECTOR_INDEX_TYPE_NONE; }  // vector_index.h:238
 
   int64_t Id() const { return id; }
   pb::common::VectorIndexType VectorIndexType() { return vector_index_type; }

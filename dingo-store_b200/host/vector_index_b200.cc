@@ -2,6 +2,7 @@
 #include "vector_index_b200.h"
 
 #include <algorithm>
+#include <cstdint>
 #include <cstring>
 #include <string>
 #include <unordered_set>
@@ -87,9 +88,11 @@ butil::Status VectorIndexB200::GetMemorySize(int64_t& m) { return ToStatus(index
 
 bool VectorIndexB200::IsExceedsMaxElements(int64_t vector_size) {  // hnsw.cc:540-550; faiss types: never
   if (vector_index_type != pb::common::VECTOR_INDEX_TYPE_HNSW) return false;
-  int64_t count = 0;
-  if (!index_ || b200vs_count(index_, &count) != B200VS_OK) return true;
-  return count + vector_size > vector_index_parameter.hnsw_parameter().max_elements();
+  // hnswlib's cur_element_count includes tombstoned nodes (markDelete frees nothing) and so does the library's own
+  // capacity check: gate on live + deleted so the service never admits a write the index then rejects
+  int64_t count = 0, deleted = 0;
+  if (!index_ || b200vs_count(index_, &count) != B200VS_OK || b200vs_deleted_count(index_, &deleted) != B200VS_OK) return true;
+  return count + deleted + vector_size > vector_index_parameter.hnsw_parameter().max_elements();
 }
 
 butil::Status VectorIndexB200::AddOrUpsert(const std::vector<pb::common::VectorWithId>& vs, bool is_upsert) {
@@ -167,7 +170,7 @@ static butil::Status LowerFilters(b200vs_index* index, const std::vector<std::sh
 }
 
 butil::Status VectorIndexB200::Search(const std::vector<pb::common::VectorWithId>& vs, uint32_t topk,
-                                      const std::vector<std::shared_ptr<FilterFunctor>>& filters, bool /*reconstruct*/,
+                                      const std::vector<std::shared_ptr<FilterFunctor>>& filters, bool reconstruct,
                                       const pb::common::VectorSearchParameter& parameter,
                                       std::vector<pb::index::VectorWithDistanceResult>& results) {
   if (vs.empty()) return butil::Status(pb::error::EILLEGAL_PARAMTETERS, "vector_with_ids is empty");  // flat.cc:208-210
@@ -188,6 +191,18 @@ butil::Status VectorIndexB200::Search(const std::vector<pb::common::VectorWithId
   std::vector<int64_t> labels((size_t)topk * vs.size(), -1);  // flat.cc:218-219
   const int rc = b200vs_search(index_, (int64_t)vs.size(), x.data(), (int32_t)topk, &lf.sp, distances.data(), labels.data());
   if (rc != B200VS_OK) return ToStatus(rc);
+  // reconstruct: only the HNSW plugin honours it, and never for cosine (hnsw.cc:383-395, :469-472 "force reconstruct false");
+  // the faiss plugins ignore the flag (flat.cc:205, ivf_flat.cc:191)
+  std::vector<float> stored;
+  std::vector<uint8_t> found;
+  if (reconstruct && vector_index_type == pb::common::VECTOR_INDEX_TYPE_HNSW && metric_type_ != pb::common::METRIC_TYPE_COSINE) {
+    stored.resize(labels.size() * (size_t)dimension_);
+    found.assign(labels.size(), 0);
+    std::vector<int64_t> ask(labels);
+    for (auto& l : ask) if (l < 0) l = INT64_MIN;  // never a stored id
+    const int rrc = b200vs_reconstruct(index_, (int64_t)ask.size(), ask.data(), stored.data(), found.data());
+    if (rrc != B200VS_OK) return ToStatus(rrc);
+  }
   // FillSearchResult, utils.cc:611-655: one result per query appended; label < 0 skipped; distances arrive in API semantics
   for (size_t row = 0; row < vs.size(); ++row) {
     auto& result = results.emplace_back();
@@ -199,11 +214,25 @@ butil::Status VectorIndexB200::Search(const std::vector<pb::common::VectorWithId
       vwi->set_id(labels[pos]);
       vwi->mutable_vector()->set_dimension(dimension_);
       vwi->mutable_vector()->set_value_type(pb::common::ValueType::FLOAT);
+      if (!found.empty()) {
+        if (!found[pos]) return butil::Status(pb::error::EINTERNAL, "getDataByLabel failed, label: " + std::to_string(labels[pos]));  // hnsw.cc:389-394
+        for (int32_t j = 0; j < dimension_; ++j) vwi->mutable_vector()->add_float_values(stored[pos * (size_t)dimension_ + j]);
+      }
       vwd->set_distance(distances[pos]);
       vwd->set_metric_type(metric_type_);
     }
   }
   return butil::Status::OK();
+}
+
+// VectorIndexIvfPq::VectorIndexSubType (vector_index_ivf_pq.cc:474): FLAT while the inner Flat index serves, IVF_PQ after.
+pb::common::VectorIndexType VectorIndexB200::VectorIndexSubType() {
+  if (vector_index_type != pb::common::VECTOR_INDEX_TYPE_IVF_PQ || !index_) return pb::common::VECTOR_INDEX_TYPE_NONE;  // base default, vector_index.h:238
+  switch (b200vs_sub_type(index_)) {
+    case B200VS_FLAT: return pb::common::VECTOR_INDEX_TYPE_FLAT;
+    case B200VS_IVF_PQ: return pb::common::VECTOR_INDEX_TYPE_IVF_PQ;
+    default: return pb::common::VECTOR_INDEX_TYPE_NONE;
+  }
 }
 
 butil::Status VectorIndexB200::RangeSearch(const std::vector<pb::common::VectorWithId>& vs, float radius,

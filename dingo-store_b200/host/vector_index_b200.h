@@ -62,6 +62,7 @@ class VectorIndexB200 : public VectorIndex {
   // fork()-based saving (vector_index_snapshot_manager.cc:583-608) cannot carry a CUDA context into the child:
   // report "no save support" like the DiskANN plugin (vector_index_diskann.cc:267); the server rebuilds from RocksDB.
   bool SupportSave() override { return false; }
+  pb::common::VectorIndexType VectorIndexSubType() override;  // vector_index.h:238
 
   // largest result count RangeSearch keeps per query (FLAGS_vector_index_max_range_search_result_count, vector_reader.cc:60)
   static int32_t max_range_search_result_count;

@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "b200vs_save", "b200vs_load", "b200vs_export_lists", "b200vs_merge_topk_device", "b200vs_last_search_stats", "b200vs_last_phase_times", "b200vs_calc_distance",
     "b200vs_scan_begin", "b200vs_scan_push", "b200vs_scan_finish", "b200vs_scan_abort", "b200vs_set_profiling",
     "b200vs_last_error", "b200vs_version",
-    "b200vs_add_with_ids_device", "b200vs_assign_device", "b200vs_reserve_lists", "b200vs_export_list", "b200vs_set_coalescing",
+    "b200vs_add_with_ids_device", "b200vs_assign_device", "b200vs_reserve_lists", "b200vs_export_list", "b200vs_set_coalescing", "b200vs_reconstruct", "b200vs_sub_type",
     "b200vs_shard_unique_id", "b200vs_shard_create", "b200vs_shard_destroy", "b200vs_shard_list_range", "b200vs_shard_train",
     "b200vs_shard_broadcast_state", "b200vs_shard_add", "b200vs_shard_add_device", "b200vs_shard_plan_add_device",
     "b200vs_shard_plan_commit", "b200vs_shard_search", "b200vs_shard_search_device",
@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
 class Params(ctypes.Structure):
     _fields_ = [("nlist", ctypes.c_int32), ("pq_m", ctypes.c_int32), ("pq_nbits", ctypes.c_int32),
                 ("hnsw_m", ctypes.c_int32), ("hnsw_efc", ctypes.c_int32), ("max_elements", ctypes.c_int64),
-                ("device", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("device", ctypes.c_int32), ("hnsw_build_threads", ctypes.c_int32)]
 
 
 class SearchParams(ctypes.Structure):
@@ -104,6 +104,8 @@ def lib():
     L.b200vs_reserve_lists.argtypes = [vp, vp, i32]
     L.b200vs_export_list.argtypes = [vp, i32, i64, vp, vp, ctypes.POINTER(i64)]
     L.b200vs_set_coalescing.argtypes = [vp, ctypes.c_int, ctypes.POINTER(i64 * 2)]
+    L.b200vs_reconstruct.argtypes = [vp, i64, vp, vp, vp]
+    L.b200vs_sub_type.argtypes = [vp]
     L.b200vs_shard_unique_id.argtypes = [vp]
     L.b200vs_shard_create.argtypes = [vp, i32, i32, vp, i32, ctypes.POINTER(vp)]
     L.b200vs_shard_destroy.argtypes = [vp]
@@ -154,10 +156,10 @@ class Index:
     (src/vector/vector_index.h:148-202): train / add / upsert / delete / search / range_search / get_count ..."""
 
     def __init__(self, index_type, metric, dim, nlist=0, pq_m=0, pq_nbits=0, hnsw_m=0, hnsw_efc=0, max_elements=0,
-                 device=0):
+                 device=0, hnsw_build_threads=0):
         self.L = lib()
         self.dim, self.type, self.metric = int(dim), int(index_type), int(metric)
-        p = Params(nlist, pq_m, pq_nbits, hnsw_m, hnsw_efc, max_elements, device, 0)
+        p = Params(nlist, pq_m, pq_nbits, hnsw_m, hnsw_efc, max_elements, device, hnsw_build_threads)
         self.params = p
         h = ctypes.c_void_p()
         _check(self.L.b200vs_create(index_type, metric, dim, ctypes.byref(p), ctypes.byref(h)))
@@ -298,6 +300,16 @@ class Index:
                                           codes.ctypes.data if codes is not None and codes.size else None,
                                           ids.ctypes.data if ids.size else None))
         return off, vec, codes, ids
+
+    def reconstruct(self, ids):
+        ids = _i64(ids)
+        out = np.zeros((ids.size, self.dim), dtype=np.float32)
+        found = np.zeros(ids.size, dtype=np.uint8)
+        _check(self.L.b200vs_reconstruct(self.h, ids.size, ids.ctypes.data, out.ctypes.data, found.ctypes.data))
+        return out, found.astype(bool)
+
+    def sub_type(self):
+        return int(self.L.b200vs_sub_type(self.h))
 
     def coalescing(self, on=-1):
         """Switch (1 / 0) or just read (-1) request coalescing; returns (batches run, requests served)."""

@@ -58,7 +58,9 @@ typedef struct {
   int32_t hnsw_efc;     /* efconstruction */
   int64_t max_elements; /* hnsw max_elements */
   int32_t device;       /* CUDA device ordinal */
-  int32_t reserved;
+  int32_t hnsw_build_threads; /* host threads inserting a batch into the HNSW graph.  0 / 1 = single writer (deterministic
+                               * graph, equal to the oracle's); > 1 = concurrent insertion with per-node locks, what the
+                               * reference does with its 16-thread pool (vector_index_hnsw.cc:229-243: graph differs run to run) */
 } b200vs_params;
 
 /* search-time parameters: pb::common::VectorSearchParameter knobs (ivf_flat().nprobe() ivf_flat.cc:211,
@@ -116,6 +118,16 @@ int b200vs_search_device(b200vs_index* idx, int64_t nq, const float* xq_dev, int
  * query are kept (closest first); out_counts[nq] receives the per-query hit count. */
 int b200vs_range_search(b200vs_index* idx, int64_t nq, const float* xq, float radius, int32_t max_results,
                         const b200vs_search_params* sp, float* out_dist, int64_t* out_ids, int32_t* out_counts);
+
+/* Stored vectors by id — what VectorIndexHnsw::Search returns per hit when reconstruct = true (hnswlib getDataByLabel,
+ * vector_index_hnsw.cc:383-395; cosine indexes never reconstruct, :469-472).  out [n, dim]; found[n] = 1 / 0 (unknown or
+ * deleted id: row left untouched).  Implemented for HNSW and FLAT. */
+int b200vs_reconstruct(b200vs_index* idx, int64_t n, const int64_t* ids, float* out, uint8_t* found);
+
+/* VectorIndex::VectorIndexSubType (vector_index.h:238; vector_index_ivf_pq.cc:474): for IVF_PQ the index type actually
+ * serving searches — B200VS_FLAT while the inner Flat index is in use, B200VS_IVF_PQ once trained on enough data; -1 =
+ * untrained.  Other types return their own type. */
+int b200vs_sub_type(b200vs_index* idx);
 
 /* GetCount / GetDeletedCount / GetMemorySize / IsTrained / NeedTrain — vector_index.h:150-152,:199-200 */
 int b200vs_count(b200vs_index* idx, int64_t* count);

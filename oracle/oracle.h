@@ -101,6 +101,7 @@ int oracle_hnsw_search(oracle_hnsw*, int64_t nq, const float* xq, int32_t k, int
 /* export the graph in the flat layout the GPU index loads (see include/b200vs.h, B200VS_STATE_HNSW) */
 int64_t oracle_hnsw_export_size(oracle_hnsw*);
 int oracle_hnsw_export(oracle_hnsw*, void* blob, int64_t len);
+int oracle_hnsw_import(oracle_hnsw*, const void* blob, int64_t len);  /* search a graph built elsewhere (same layout as export) */
 
 /* harness utility: multi-threaded first-touch copy (NUMA-spread pages for the timed CPU baseline) */
 void oracle_parallel_copy(void* dst, const void* src, size_t bytes, int nthreads);

@@ -345,4 +345,31 @@ int oracle_hnsw_export(oracle_hnsw* h, void* blob, int64_t len) {
   return 0;
 }
 
+// Load a graph in the export layout (a graph built elsewhere, e.g. by the engine's concurrent builder whose insertion
+// order — like the reference's 16-thread build, vector_index_hnsw.cc:229-243 — is not reproducible): the oracle then
+// SEARCHES exactly that graph.  Returns 0, or -1 when the blob does not fit this oracle's (d, M, max_elements).
+int oracle_hnsw_import(oracle_hnsw* h, const void* blob, int64_t len) {
+  if (len < 64) return -1;
+  const char* base = (const char*)blob;
+  const int64_t* hdr = (const int64_t*)base;
+  const int64_t n = hdr[1];
+  if (hdr[0] != 0x57534E48 || hdr[2] != h->d || hdr[3] != (int64_t)h->M || n > h->max_elements) return -1;
+  const char* p = base + 64;
+  memcpy(h->levels.data(), p, n * 4); p += n * 4;
+  p = base + ((p - base) + 7) / 8 * 8;
+  const int64_t* off = (const int64_t*)p; p += (n + 1) * 8;
+  memcpy(h->link0.data(), p, (size_t)n * (h->maxM0 + 1) * 4); p += (size_t)n * (h->maxM0 + 1) * 4;
+  for (int64_t i = 0; i < n; ++i) h->linkup[i].assign((const tableint*)p + off[i], (const tableint*)p + off[i + 1]);
+  p += off[n] * 4;
+  p = base + ((p - base) + 7) / 8 * 8;
+  memcpy(h->data.data(), p, (size_t)n * h->d * 4); p += (size_t)n * h->d * 4;
+  p = base + ((p - base) + 7) / 8 * 8;
+  if ((p - base) + n * 8 > len) return -1;
+  memcpy(h->labels.data(), p, n * 8);
+  h->cur = n; h->maxlevel = (int)hdr[5]; h->enterpoint = (tableint)hdr[6];
+  h->lookup.clear();
+  for (int64_t i = 0; i < n; ++i) h->lookup[h->labels[i]] = (tableint)i;
+  return 0;
+}
+
 }  // extern "C"

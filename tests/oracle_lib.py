@@ -61,6 +61,7 @@ class Oracle:
         L.oracle_hnsw_export_size.argtypes = [vp]
         L.oracle_hnsw_export_size.restype = i64
         L.oracle_hnsw_export.argtypes = [vp, vp, i64]
+        L.oracle_hnsw_import.argtypes = [vp, vp, i64]
         L.oracle_version.restype = ctypes.c_char_p
         L.oracle_parallel_copy.argtypes = [vp, vp, sz, ctypes.c_int]
         self.L = L
@@ -215,6 +216,12 @@ class OracleHnsw:
                                          D.ctypes.data, I.ctypes.data, nd.ctypes.data, nh.ctypes.data)
         assert rc == 0
         return D, I, nd, nh
+
+    def load(self, blob):
+        """Adopt a graph in the export layout (e.g. the engine's b200vs_get_trained_state): searches then run on that graph."""
+        b = np.ascontiguousarray(blob, dtype=np.uint8)
+        rc = self.o.L.oracle_hnsw_import(self.h, b.ctypes.data, b.nbytes)
+        assert rc == 0, rc
 
     def export(self):
         n = self.o.L.oracle_hnsw_export_size(self.h)

@@ -88,3 +88,59 @@ def test_status_codes_sticky_ef_and_deletes(oracle):
     D3, I3 = ix.search(xq, 10, efsearch=100)
     assert not (set(I3.ravel()) & set(dead))
     assert (I3 >= 0).all()
+
+
+@pytest.mark.parametrize("metric", [L2, COSINE])
+@pytest.mark.parametrize("M", [24, 40, 64])
+def test_wide_link_lists(oracle, metric, M):
+    """nlinks > 16 (level-0 lists of up to 2 * nlinks = 128 neighbours): the reference constructor takes any nlinks
+    (vector_index_hnsw.cc:135-184); the kernel walks a list 32 neighbours at a time."""
+    ix, h, xb, labels = pair(oracle, metric, 2500, 48, M=M, efc=120, seed=M)
+    assert np.array_equal(ix.get_trained_state(), h.export())
+    xq = np.random.default_rng(M).random((33, 48)).astype(np.float32)
+    for k, ef in ((10, 64), (50, 0), (1, 300)):
+        Dg, Ig = ix.search(xq, k, efsearch=ef)
+        Do, Io, _, _ = h.search(xq, k, ef=ef, nthreads=8)
+        assert_same_results(Dg, Ig, Do, Io)
+
+
+def test_reconstruct_returns_stored_vectors(oracle):
+    """hnswlib getDataByLabel behind Search(reconstruct = true), vector_index_hnsw.cc:383-395."""
+    ix, h, xb, labels = pair(oracle, L2, 800, 20, seed=5)
+    D, I = ix.search(xb[:5], 3, efsearch=50)
+    vec, found = ix.reconstruct(I.ravel())
+    assert found.all()
+    pos = I.ravel() - 1000
+    assert np.array_equal(vec, xb[pos])
+    ix.delete(labels[:1])
+    _, found = ix.reconstruct(np.array([labels[0], 424242], dtype=np.int64))
+    assert not found.any()
+    # cosine stores the hnsw-normalised rows (the reference never reconstructs for cosine, :469-472)
+    ic, hc, xc, lc = pair(oracle, COSINE, 300, 16, seed=6)
+    vec, found = ic.reconstruct(lc[:4])
+    assert found.all() and np.allclose(np.linalg.norm(vec, axis=1), 1.0, atol=1e-5)
+
+
+def test_concurrent_build_graph_is_searched_exactly(oracle):
+    """hnsw_build_threads > 1 = the reference's concurrent addPoint (vector_index_hnsw.cc:229-243): the graph depends on thread
+    timing, so parity is defined on the graph itself — the oracle adopts it (oracle_hnsw_import) and both sides must walk it
+    identically; the graph must also be a sound HNSW (every live row reachable in practice: self queries come back first)."""
+    rng = np.random.default_rng(8)
+    n, d, M, efc = 20000, 64, 16, 100
+    xb = rng.random((n, d)).astype(np.float32)
+    labels = np.arange(1, n + 1, dtype=np.int64)
+    ix = b200vs.Index(HNSW, L2, d, hnsw_m=M, hnsw_efc=efc, max_elements=n, hnsw_build_threads=16)
+    for a in range(0, n, 5000):
+        ix.add(xb[a:a + 5000], labels[a:a + 5000])
+    assert ix.get_count() == n
+    h = oracle_lib.OracleHnsw(oracle, L2, d, n, M, efc)
+    h.load(ix.get_trained_state())
+    xq = rng.random((100, d)).astype(np.float32)
+    Dg, Ig = ix.search(xq, 10, efsearch=128)
+    Do, Io, _, _ = h.search(xq, 10, ef=128, nthreads=8)
+    assert_same_results(Dg, Ig, Do, Io)
+    Dg, Ig = ix.search(xb[:200], 1, efsearch=64)
+    assert (Ig[:, 0] == labels[:200]).mean() > 0.99
+    Df, If = oracle.flat_search(oracle_lib.L2, xb, labels, xq, 10, nthreads=8)
+    Dg, Ig = ix.search(xq, 10, efsearch=200)
+    assert np.mean([len(set(a) & set(b)) / 10 for a, b in zip(Ig, If)]) > 0.9  # a healthy graph: recall vs brute force

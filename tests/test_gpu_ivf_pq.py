@@ -106,3 +106,34 @@ def test_upsert_delete_filters(oracle):
     with pytest.raises(b200vs.B200VSError) as e:
         ix.delete(np.array([999999]))
     assert e.value.code == b200vs.EVECTOR_INVALID
+
+
+@pytest.mark.parametrize("metric", [L2, IP, COSINE])
+def test_range_search_on_codes(oracle, metric):
+    """VectorIndexRawIvfPq::RangeSearch (vector_index_raw_ivf_pq.cc:212-278): the LUT scan with a radius instead of top-k.
+    Checked against the oracle's LUT distances of every probed row (top-k with k = all candidates), thresholded on the host."""
+    n, d, nlist, M, nprobe, nq = 9000, 64, 16, 8, 6, 9
+    ix, xb, stored, ids, cent, cb, asg = build(oracle, metric, n, d, nlist, M, seed=11)
+    off, _, codes, lids = ix.export_lists(nlist, with_vectors=False, code_size=M)
+    xq = np.random.default_rng(12).standard_normal((nq, d)).astype(np.float32)
+    kall = 4096
+    Do, Io = oracle.ivfpq_search(metric, cent, cb, off, codes, lids, xq, kall, nprobe, nthreads=8)  # API distances, ascending
+    # a radius that keeps a few dozen hits per query
+    radius = float(np.sort(Do[Io >= 0])[nq * 40])
+    D, I, C = ix.range_search(xq, radius, 256, nprobe=nprobe)
+    for q in range(nq):
+        valid = Io[q] >= 0
+        # faiss range_search is strict on the RAW metric: L2 dis < radius ; IP ip > 1 - radius  <=>  1 - ip < radius up to rounding of (1 - x)
+        raw = Do[q][valid] if metric == L2 else 1.0 - Do[q][valid]
+        keep = raw < radius if metric == L2 else raw > np.float32(1.0) - np.float32(radius)
+        want_i, want_d = Io[q][valid][keep], Do[q][valid][keep]
+        assert C[q] == min(len(want_i), 256)
+        assert np.array_equal(I[q, :C[q]], want_i[:C[q]])
+        assert np.array_equal(D[q, :C[q]].view(np.uint32), want_d[:C[q]].view(np.uint32))
+        assert (I[q, C[q]:] == -1).all()
+    # filters ride along; an untrained index answers with empty results
+    D2, I2, C2 = ix.range_search(xq, radius, 256, nprobe=nprobe, id_range=(1, 2000))
+    assert ((I2 < 2000) | (I2 == -1)).all() and (C2 <= C).all()
+    fresh = b200vs.Index(IVF_PQ, metric, d, nlist=nlist, pq_m=M, pq_nbits=8)
+    D3, I3, C3 = fresh.range_search(xq, radius, 16)
+    assert (C3 == 0).all() and (I3 == -1).all()
