@@ -12,6 +12,9 @@
 //
 // Replaces faiss exhaustive_{L2sqr,inner_product}_seq + HeapBlockResultHandler behind VectorIndexFlat::Search
 // (src/vector/vector_index_flat.cc:249-252) for nq < 16.
+#include <cstdio>
+#include <cstdlib>
+
 #include "flat_small.cuh"
 #include "scan_kernels.cuh"
 #include "warp_select.cuh"
@@ -36,6 +39,7 @@ struct FsArgs {
   int* tickets;          // [nq] zeroed before the launch
   float* out_dist;       // [nq, k] API semantics
   long long* out_ids;    // [nq, k]
+  long long* dbg;        // optional [8] clock64 stamps of slice 0 and of the merging CTA (B200VS_FS_DEBUG)
 };
 
 __device__ __forceinline__ long long warp_min_ll(long long v) {
@@ -44,64 +48,76 @@ __device__ __forceinline__ long long warp_min_ll(long long v) {
   return v;
 }
 
-// top-k (ascending (key, id)) of n (key, id) pairs in shared memory, executed by ONE warp; emit(rank, kd, id) receives the
-// result.  Usual case: the k-th key kth is found by a radix select and the <= FS_CT pairs with key <= kth are rank-sorted.
-// Mass ties (more than FS_CT pairs share the k-th key: duplicated vectors): the pairs strictly below kth are kept and the
-// open slots are filled with the smallest ids among the tied pairs, one warp-min per slot — same (key, id) order, no limit.
+// top-k (ascending (key, id)) of n (key, id) pairs in shared memory, by ALL threads of the CTA; emit(rank, kd, id) receives
+// the result; returns how many live pairs were emitted.  Usual case: the k-th key kth comes from a block-wide radix select and
+// the <= FS_CT pairs with key <= kth are rank-sorted.  Mass ties (more than FS_CT pairs share the k-th key: duplicated
+// vectors): the pairs strictly below kth are kept and the open slots are filled with the smallest ids among the tied pairs,
+// one warp-min per slot (warp 0) — same (key, id) order, no limit on the number of duplicates.
+struct FsShared {
+  BlockSelShared sel;
+  uint32_t ckd[FS_CT];
+  long long cid[FS_CT];
+  int m;
+};
 template <class Emit>
-__device__ __forceinline__ int fs_topk_warp(const uint32_t* kd, const long long* id, int n, int k, int* hist, uint32_t* ckd, long long* cid, Emit emit) {
+__device__ __forceinline__ int fs_topk_block(const uint32_t* kd, const long long* id, int n, int k, FsShared& F, Emit emit) {
   const int lane = threadIdx.x & 31;
   uint32_t kth = 0xFFFFFFFFu;
-  if (n > k) {
-    int c_le;
-    kth = warp_kth_key(k, hist, [&](auto f) { for (int i = lane; i < n; i += 32) f(kd[i]); }, c_le);
-  }
-  int m = 0;
-  for (int base = 0; base < n; base += 32) {
-    const int i = base + lane;
+  if (n > k) kth = block_kth_key_any(k, F.sel, [&](auto f) { for (int i = threadIdx.x; i < n; i += blockDim.x) f(kd[i]); });
+  if (threadIdx.x == 0) F.m = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
     const bool in = i < n && kd[i] <= kth && !(kd[i] == KEY_SENTINEL_D && id[i] == KEY_SENTINEL_ID);  // empty slots never surface
     const unsigned msk = __ballot_sync(0xffffffffu, in);
-    const int p = m + __popc(msk & ((1u << lane) - 1u));
-    if (in && p < FS_CT) { ckd[p] = kd[i]; cid[p] = id[i]; }
-    m += __popc(msk);
+    int wbase = 0;
+    if (lane == 0 && msk) wbase = atomicAdd(&F.m, __popc(msk));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    const int p = wbase + __popc(msk & ((1u << lane) - 1u));
+    if (in && p < FS_CT) { F.ckd[p] = kd[i]; F.cid[p] = id[i]; }
   }
-  __syncwarp();
-  if (m > FS_CT) {  // mass ties at the k-th key
-    m = 0;
-    for (int base = 0; base < n; base += 32) {
-      const int i = base + lane;
-      const bool in = i < n && kd[i] < kth;
-      const unsigned msk = __ballot_sync(0xffffffffu, in);
-      if (in) { const int p = m + __popc(msk & ((1u << lane) - 1u)); ckd[p] = kd[i]; cid[p] = id[i]; }  // fewer than k such pairs
-      m += __popc(msk);
+  __syncthreads();
+  int m = F.m;
+  if (m > FS_CT) {  // mass ties at the k-th key: warp 0 resolves them
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      m = 0;
+      for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const bool in = i < n && kd[i] < kth;
+        const unsigned msk = __ballot_sync(0xffffffffu, in);
+        if (in) { const int p = m + __popc(msk & ((1u << lane) - 1u)); F.ckd[p] = kd[i]; F.cid[p] = id[i]; }  // fewer than k such pairs
+        m += __popc(msk);
+      }
+      long long last = (long long)0x8000000000000000LL;
+      for (; m < k; ++m) {
+        long long best = KEY_SENTINEL_ID;
+        for (int i = lane; i < n; i += 32) if (kd[i] == kth && id[i] > last && id[i] < best) best = id[i];
+        best = warp_min_ll(best);
+        if (best == KEY_SENTINEL_ID) break;
+        if (lane == 0) { F.ckd[m] = kth; F.cid[m] = best; }
+        last = best;
+      }
+      if (lane == 0) F.m = m;
     }
-    long long last = (long long)0x8000000000000000LL;
-    for (; m < k; ++m) {
-      long long best = KEY_SENTINEL_ID;
-      for (int i = lane; i < n; i += 32) if (kd[i] == kth && id[i] > last && id[i] < best) best = id[i];
-      best = warp_min_ll(best);
-      if (best == KEY_SENTINEL_ID) break;
-      if (lane == 0) { ckd[m] = kth; cid[m] = best; }
-      last = best;
-    }
-    __syncwarp();
+    __syncthreads();
+    m = F.m;
   }
-  warp_rank_sort(ckd, cid, m, [&](int rank, int e) { if (rank < k) emit(rank, ckd[e], cid[e]); });
+  block_rank_sort(F.ckd, F.cid, m, [&](int rank, int e) { if (rank < k) emit(rank, F.ckd[e], F.cid[e]); });
   return min(m, k);
 }
 
 template <bool L2>
 static __global__ void __launch_bounds__(FS_THREADS) flat_small_kernel(const FsArgs a) {
   extern __shared__ __align__(16) unsigned char fs_smem[];  // [FS_PAIRS] ids, [FS_PAIRS] keys, then the query row
-  __shared__ int s_hist[WS_BINS];
-  __shared__ uint32_t s_ckd[FS_CT];
-  __shared__ long long s_cid[FS_CT];
+  __shared__ FsShared F;
   __shared__ int s_n, s_last;
   long long* s_id = reinterpret_cast<long long*>(fs_smem);
   uint32_t* s_kd = reinterpret_cast<uint32_t*>(fs_smem + (size_t)FS_PAIRS * 8);
   float* qs = reinterpret_cast<float*>(fs_smem + (size_t)FS_PAIRS * 12);
   const int qi = blockIdx.y, slice = blockIdx.x, nslices = gridDim.x;
   const int d = a.d, k = a.k;
+  const long long t_start = clock64();
   for (int i = threadIdx.x; i < d; i += FS_THREADS) qs[i] = a.queries[(size_t)qi * d + i];
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
@@ -122,20 +138,23 @@ static __global__ void __launch_bounds__(FS_THREADS) flat_small_kernel(const FsA
     if (valid && t == 0) { const int p = wbase + __popc(wm & ((1u << (threadIdx.x & 31)) - 1u)); s_kd[p] = f2ord(L2 ? v : -v); s_id[p] = id; }
   }
   __syncthreads();
+  const long long t_scan = clock64();
   uint32_t* pk = a.part_kd + ((size_t)qi * nslices + slice) * k;
   long long* pi = a.part_id + ((size_t)qi * nslices + slice) * k;
-  if (threadIdx.x < 32) {
+  {
     const int n = s_n;
-    const int have = fs_topk_warp(s_kd, s_id, n, k, s_hist, s_ckd, s_cid, [&](int rank, uint32_t kd, long long id) { pk[rank] = kd; pi[rank] = id; });
-    for (int i = have + (int)threadIdx.x; i < k; i += 32) { pk[i] = KEY_SENTINEL_D; pi[i] = KEY_SENTINEL_ID; }
-    __syncwarp();
+    const int have = fs_topk_block(s_kd, s_id, n, k, F, [&](int rank, uint32_t kd, long long id) { pk[rank] = kd; pi[rank] = id; });
+    for (int i = have + (int)threadIdx.x; i < k; i += FS_THREADS) { pk[i] = KEY_SENTINEL_D; pi[i] = KEY_SENTINEL_ID; }
+    __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
       s_last = atomicAdd(a.tickets + qi, 1) == nslices - 1 ? 1 : 0;
     }
   }
   __syncthreads();
+  if (a.dbg && slice == 0 && threadIdx.x == 0) { a.dbg[0] = t_scan - t_start; a.dbg[1] = clock64() - t_scan; }
   if (!s_last) return;
+  const long long t_merge0 = clock64();
   // ---- the CTA that finished last merges the per-slice lists of this query: no second launch ----
   __threadfence();
   const int tot = nslices * k;  // <= FS_PAIRS (launcher)
@@ -143,15 +162,16 @@ static __global__ void __launch_bounds__(FS_THREADS) flat_small_kernel(const FsA
   const long long* alli = a.part_id + (size_t)qi * nslices * k;
   for (int j = threadIdx.x; j < tot; j += FS_THREADS) { s_kd[j] = __ldcg(allk + j); s_id[j] = __ldcg(alli + j); }  // empty slots carry the sentinel pair
   __syncthreads();
-  if (threadIdx.x < 32) {
+  {
     const int n = tot;
-    const int have = fs_topk_warp(s_kd, s_id, n, k, s_hist, s_ckd, s_cid, [&](int rank, uint32_t kd, long long id) {
+    const int have = fs_topk_block(s_kd, s_id, n, k, F, [&](int rank, uint32_t kd, long long id) {
       const float v = ord2f(kd);
       const float raw = L2 ? v : -v;
       a.out_dist[(size_t)qi * k + rank] = L2 ? raw : __fsub_rn(1.0f, raw);
       a.out_ids[(size_t)qi * k + rank] = id;
     });
-    for (int i = have + (int)threadIdx.x; i < k; i += 32) { a.out_dist[(size_t)qi * k + i] = 0.f; a.out_ids[(size_t)qi * k + i] = -1; }
+    for (int i = have + (int)threadIdx.x; i < k; i += FS_THREADS) { a.out_dist[(size_t)qi * k + i] = 0.f; a.out_ids[(size_t)qi * k + i] = -1; }
+    if (a.dbg && threadIdx.x == 0) { a.dbg[2] = clock64() - t_merge0; a.dbg[3] = t_merge0 - t_start; a.dbg[4] = slice; }
   }
 }
 
@@ -181,6 +201,8 @@ void flat_small_search(IndexBase* ix, bool l2, const float* vecs, const long lon
   a.part_id = S.alloc<long long>((size_t)nq * nslices * k);
   a.tickets = S.alloc<int>(nq);
   a.out_dist = out_dist; a.out_ids = out_ids;
+  static const bool debug = getenv("B200VS_FS_DEBUG") != nullptr;
+  a.dbg = debug ? S.alloc<long long>(8) : nullptr;
   B200VS_CUDA(cudaMemsetAsync(a.tickets, 0, (size_t)nq * 4, s));
   const size_t smem = (size_t)FS_PAIRS * 12 + ((size_t)d * 4 + 15) / 16 * 16;
   dim3 grid(nslices, (unsigned)nq);
@@ -188,6 +210,13 @@ void flat_small_search(IndexBase* ix, bool l2, const float* vecs, const long lon
   else flat_small_kernel<false><<<grid, FS_THREADS, smem, s>>>(a);
   B200VS_CUDA(cudaGetLastError());
   ix->launch_count(1);
+  if (debug) {
+    long long h[8] = {0};
+    B200VS_CUDA(cudaMemcpyAsync(h, a.dbg, 40, cudaMemcpyDeviceToHost, s));
+    B200VS_CUDA(cudaStreamSynchronize(s));
+    fprintf(stderr, "[b200vs] flat_small: slice0 scan %lld clk, select+ticket %lld clk; merging CTA (slice %lld): started merge at +%lld clk, merge %lld clk; grid %d x %d, %d rows/CTA\n",
+            h[0], h[1], h[4], h[3], h[2], nslices, (int)nq, rows);
+  }
 }
 
 }  // namespace b200vs
