@@ -311,7 +311,14 @@ __device__ void h_pop(const HeapRef& h, int& n) {
 // searchBaseLayerST): it pops the closest candidate, reads its link list 32 neighbours at a time, keeps the unvisited ones in
 // list order; then ALL 32 quads of the CTA compute those rows' distances in one round (exact AVX-512 order, so the traversal
 // is the CPU traversal); lane 0 applies the heap updates in neighbour order.  Two block barriers per batch of <= 32 neighbours.
-template <bool L2>
+// FAST (no id filter, no tombstones — every accepted neighbour enters both of hnswlib's queues): the two binary heaps collapse
+// into ONE ascending array T of the best <= ef nodes with an "expanded" flag per entry.  The next candidate is the first
+// unexpanded entry of T; a hop's <= 32 scored neighbours are merged into T by all 128 threads at once (each thread places one
+// old entry and at most one new one at its rank), instead of ~30 sift-up / sift-down sequences executed by a single lane at one
+// dependent instruction per ~25 ns — that lone-lane heap work was 80 % of a hop.  The visited set, the order in which nodes
+// are expanded and the returned ids / distances are those of searchBaseLayerST (exact-distance ties between different nodes,
+// which std::priority_queue orders by heap position, are the one place the two can differ).
+template <bool L2, bool FAST>
 __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_kernel(const HnswDev g, const float* __restrict__ queries, long long nq,
                                                                   int k, int ef, FilterDev filt, unsigned int* visited /*[nq, words]*/,
                                                                   long long words, HeapEnt* cand_pool, int cand_cap, float* out_dist,
@@ -376,6 +383,91 @@ __global__ void __launch_bounds__(HNSW_THREADS) hnsw_search_kernel(const HnswDev
         }
       }
     }
+  }
+  if (FAST) {
+    // ---- base layer, merged-array form.  T = cand_sm region reused: [2][ef] entries (id bit 31 = expanded) ----
+    HeapEnt* T = top_sm;            // [ef + 1]
+    HeapEnt* T2 = cand_sm;          // [>= ef + 1] (HNSW_CAND_SMEM >= ef + 1 is checked on the host)
+    int ntop = 1;
+    if (threadIdx.x == 0) { T[0].d = curdist; T[0].id = cur; vis[cur >> 5] |= 1u << (cur & 31); }
+    unsigned int node = 0;
+    int size = 0, c0 = 0;
+    bool expanding = false;
+    for (;;) {
+      __syncthreads();  // (A) T complete, s_d / s_id of the previous round consumed
+      if (warp == 0) {
+        int m = -1;
+        for (;;) {
+          if (!expanding) {
+            int idx = -1;
+            for (int b0 = 0; b0 < ntop && idx < 0; b0 += 32) {  // first unexpanded entry = closest open candidate
+              const int i = b0 + lane;
+              const bool open = i < ntop && (T[i].id >> 31) == 0u;
+              const unsigned msk = __ballot_sync(0xffffffffu, open);
+              if (msk) idx = b0 + __ffs(msk) - 1;
+            }
+            if (idx < 0) { m = -1; break; }
+            node = T[idx].id;
+            __syncwarp();
+            if (lane == 0) T[idx].id = node | 0x80000000u;
+            size = (int)g.link0[(size_t)node * (g.maxM0 + 1)];
+            c0 = 0;
+            expanding = true;
+          }
+          if (c0 >= size) { expanding = false; continue; }
+          const unsigned int* l = g.link0 + (size_t)node * (g.maxM0 + 1) + 1 + c0;
+          const int cnt = min(32, size - c0);
+          c0 += 32;
+          unsigned int nb = 0;
+          bool fresh = false;
+          if (lane < cnt) { nb = l[lane]; fresh = ((vis[nb >> 5] >> (nb & 31)) & 1u) == 0u; }
+          const unsigned int mask = __ballot_sync(0xffffffffu, fresh);
+          if (fresh) {
+            atomicOr(&vis[nb >> 5], 1u << (nb & 31));
+            s_id[__popc(mask & ((1u << lane) - 1u))] = nb;
+          }
+          m = __popc(mask);
+          if (m > 0) break;
+        }
+        if (lane == 0) s_m = m;
+      }
+      __syncthreads();  // (B)
+      const int m = s_m;
+      if (m < 0) break;
+      score(m);
+      __syncthreads();  // (C) s_d complete
+      // merge the m scored neighbours into T (ascending, old entries first among equals), keep the best ef
+      for (int tix = threadIdx.x; tix < ntop; tix += HNSW_THREADS) {
+        const HeapEnt e = T[tix];
+        int c = 0;
+        for (int j = 0; j < m; ++j) c += s_d[j] < e.d ? 1 : 0;
+        if (tix + c < ef) T2[tix + c] = e;
+      }
+      if (threadIdx.x < m) {
+        const float dj = s_d[threadIdx.x];
+        int rank = 0;
+        for (int i = 0; i < m; ++i) rank += (s_d[i] < dj || (s_d[i] == dj && i < (int)threadIdx.x)) ? 1 : 0;
+        int lo = 0, hi = ntop;  // number of old entries with d <= dj
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (T[mid].d <= dj) lo = mid + 1; else hi = mid; }
+        if (rank + lo < ef) { HeapEnt e; e.d = dj; e.id = s_id[threadIdx.x]; T2[rank + lo] = e; }
+      }
+      ntop = min(ef, ntop + m);
+      HeapEnt* tmp = T; T = T2; T2 = tmp;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // emit the k best ascending by (distance, label)
+      const int have = min(ntop, k);
+      for (int i = 0; i < have; ++i) {
+        int best = i;
+        for (int j = i + 1; j < ntop && T[j].d == T[i].d; ++j)  // equal distances: smaller label first (T is ascending in d)
+          if (g.labels[T[j].id & 0x7fffffffu] < g.labels[T[best].id & 0x7fffffffu]) best = j;
+        const HeapEnt tmp = T[i]; T[i] = T[best]; T[best] = tmp;
+        out_dist[(size_t)qi * k + i] = T[i].d;
+        out_ids[(size_t)qi * k + i] = g.labels[T[i].id & 0x7fffffffu];
+      }
+      for (int i = have; i < k; ++i) { out_dist[(size_t)qi * k + i] = 0.f; out_ids[(size_t)qi * k + i] = -1; }
+    }
+    return;
   }
   // ---- base layer: searchBaseLayerST ----
   int ntop = 0, ncand = 0;
@@ -643,13 +735,15 @@ struct HnswIndex : IndexBase {
     if (smem > 200 * 1024) fail(B200VS_EILLEGAL_PARAMETERS, "efsearch / dimension too large for the search kernel");
     const unsigned grid = (unsigned)nq;
     ScopedKernelTimer timer(this, s, profiling);
-    if (g.l2) {
-      B200VS_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      hnsw_search_kernel<true><<<grid, HNSW_THREADS, smem, s>>>(g, q, nq, k, ef_run, f, visited, words, cand, cand_cap, od, oi, err);
-    } else {
-      B200VS_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      hnsw_search_kernel<false><<<grid, HNSW_THREADS, smem, s>>>(g, q, nq, k, ef_run, f, visited, words, cand, cand_cap, od, oi, err);
-    }
+    const bool fast = !(f.has_range || f.sorted_ids != nullptr) && !g.has_deletions && ef_run + 1 <= HNSW_CAND_SMEM && G.n < (1LL << 31);
+#define B200VS_HNSW_LAUNCH(L2_, FAST_)                                                                                              \
+  do {                                                                                                                             \
+    B200VS_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<L2_, FAST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));     \
+    hnsw_search_kernel<L2_, FAST_><<<grid, HNSW_THREADS, smem, s>>>(g, q, nq, k, ef_run, f, visited, words, cand, cand_cap, od, oi, err); \
+  } while (0)
+    if (g.l2) { if (fast) B200VS_HNSW_LAUNCH(true, true); else B200VS_HNSW_LAUNCH(true, false); }
+    else { if (fast) B200VS_HNSW_LAUNCH(false, true); else B200VS_HNSW_LAUNCH(false, false); }
+#undef B200VS_HNSW_LAUNCH
     timer.stop();
     B200VS_CUDA(cudaGetLastError());
     launch_count(1);

@@ -577,55 +577,56 @@ tc_tau_kernel(const long long* __restrict__ probes, const int* __restrict__ pos,
 }
 
 
-// Threshold kernel, common case (<= WT_PAIRS sampled spans of TC_SAMPLE rows per query): one 128-thread CTA per query.
-// Warp 0 walks the probe list and stages one (sample slot, column) per sampled span; every thread then fetches one span (its
-// 32 scores are one 128-byte line: 8 independent 16-byte loads, so the whole sample is in flight at once) and the CTA
-// radix-selects the k-th smallest finite score together.  Queries with more spans set redo[q]: tc_tau_kernel finishes them.
-constexpr int WT_THREADS = 128;
-constexpr int WT_PAIRS = 256;
-static __global__ void __launch_bounds__(WT_THREADS)
+// Warp-per-query form of the threshold kernel (the common case: <= WT_PAIRS sampled spans of TC_SAMPLE rows per query).
+// Lanes walk the probe list, stage one (sample slot, column) per sampled span, then the warp reads one span per step
+// (32 contiguous floats) and radix-selects the k-th smallest finite score.  Queries with more spans set redo[q] and are
+// finished by tc_tau_kernel.
+constexpr int WT_WARPS = 4;
+constexpr int WT_PAIRS = 64;
+static __global__ void __launch_bounds__(WT_WARPS * 32)
 tc_tau_warp_kernel(const long long* __restrict__ probes, const int* __restrict__ pos, const int* __restrict__ cnt,
                    const int* __restrict__ item_off, const int* __restrict__ list_len, const TcItem* __restrict__ items, int nprobe,
                    const float* __restrict__ sample, int k, int nq, int l2, const float* __restrict__ qnorm, float max_norm, int d, int cap,
                    float* tau, int* redo) {
-  __shared__ BlockSelShared S;
-  __shared__ int s_pair[WT_PAIRS];
-  __shared__ uint32_t s_val[WT_PAIRS * TC_SAMPLE];
-  __shared__ int s_np, s_nfin, s_cnt;
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x;
-  if (threadIdx.x == 0) { s_nfin = 0; s_cnt = 0; }
-  if (threadIdx.x < 32) {
-    int np = 0;
-    for (int base = 0; base < nprobe; base += 32) {
-      const int j = base + lane;
-      int nspan = 0, first = 0, ng = 1, g = 0, n = 0;
-      if (j < nprobe) {
-        const long long l = probes[(size_t)q * nprobe + j];
-        const int len = l >= 0 ? list_len[l] : 0;
-        if (len > 0) {
-          ng = (cnt[l] + TC_NQT - 1) / TC_NQT;
-          const int ps = pos[(size_t)q * nprobe + j];
-          g = ps / TC_NQT; n = ps % TC_NQT;
-          nspan = (len + TC_SPAN - 1) / TC_SPAN;
-          first = item_off[l];
-        }
+  __shared__ int s_hist[WT_WARPS][WS_BINS];
+  __shared__ int s_pair[WT_WARPS][WT_PAIRS];
+  __shared__ uint32_t s_val[WT_WARPS][WT_PAIRS * TC_SAMPLE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * WT_WARPS + warp;
+  if (q >= nq) return;
+  int np = 0;
+  for (int base = 0; base < nprobe; base += 32) {
+    const int j = base + lane;
+    int nspan = 0, first = 0, ng = 1, g = 0, n = 0;
+    if (j < nprobe) {
+      const long long l = probes[(size_t)q * nprobe + j];
+      const int len = l >= 0 ? list_len[l] : 0;
+      if (len > 0) {
+        ng = (cnt[l] + TC_NQT - 1) / TC_NQT;
+        const int ps = pos[(size_t)q * nprobe + j];
+        g = ps / TC_NQT; n = ps % TC_NQT;
+        nspan = (len + TC_SPAN - 1) / TC_SPAN;
+        first = item_off[l];
       }
-      int incl = nspan;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      const int off = np + incl - nspan;
-      for (int sp = 0; sp < nspan; ++sp)
-        if (off + sp < WT_PAIRS) s_pair[off + sp] = items[first + sp * (TC_SPAN / TC_CHUNK) * ng + g].sample_slot * TC_NQT + n;
-      np += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 0) s_np = np;
+    int incl = nspan;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const int off = np + incl - nspan;
+    for (int sp = 0; sp < nspan; ++sp)
+      if (off + sp < WT_PAIRS) s_pair[warp][off + sp] = items[first + sp * (TC_SPAN / TC_CHUNK) * ng + g].sample_slot * TC_NQT + n;
+    np += __shfl_sync(0xffffffffu, incl, 31);
   }
-  __syncthreads();
-  const int np = s_np;
-  if (np > WT_PAIRS) { if (threadIdx.x == 0) redo[q] = 1; return; }
-  for (int p = threadIdx.x; p < np; p += WT_THREADS) {
-    const float4* src = reinterpret_cast<const float4*>(sample + (size_t)s_pair[p] * TC_SAMPLE);
+  if (np > WT_PAIRS) { if (lane == 0) redo[q] = 1; return; }
+  if (lane == 0) redo[q] = 0;
+  __syncwarp();
+  // one lane per sampled span: its 32 scores are one 128-byte line, fetched as 8 independent 16-byte loads, so the whole
+  // query's sample is in flight at once (a warp-per-span loop would serialise one L2 round trip per span)
+  __shared__ int s_nfin[WT_WARPS];
+  if (lane == 0) s_nfin[warp] = 0;
+  __syncwarp();
+  for (int p = lane; p < np; p += 32) {
+    const float4* src = reinterpret_cast<const float4*>(sample + (size_t)s_pair[warp][p] * TC_SAMPLE);
     float4 v[TC_SAMPLE / 4];
 #pragma unroll
     for (int j = 0; j < TC_SAMPLE / 4; ++j) v[j] = src[j];
@@ -633,29 +634,21 @@ tc_tau_warp_kernel(const long long* __restrict__ probes, const int* __restrict__
     int c = 0;
 #pragma unroll
     for (int j = 0; j < TC_SAMPLE; ++j) c += f[j] < TC_INF ? 1 : 0;
-    int o = atomicAdd(&s_nfin, c);
+    int o = atomicAdd(&s_nfin[warp], c);
 #pragma unroll
-    for (int j = 0; j < TC_SAMPLE; ++j) if (f[j] < TC_INF) s_val[o++] = f2ord(f[j]);
+    for (int j = 0; j < TC_SAMPLE; ++j) if (f[j] < TC_INF) s_val[warp][o++] = f2ord(f[j]);
   }
-  __syncthreads();
-  const int nfin = s_nfin;
+  __syncwarp();
+  const int nfin = s_nfin[warp];
   float t = TC_INF;
   if (nfin >= k) {
-    t = ord2f(block_kth_key_any(k, S, [&](auto f) { for (int i = threadIdx.x; i < nfin; i += WT_THREADS) f(s_val[i]); }));
-    auto count_le = [&](float lim) {  // block-wide count of sampled scores <= lim (all threads call)
-      __syncthreads();
-      if (threadIdx.x == 0) s_cnt = 0;
-      __syncthreads();
-      int c = 0;
-      for (int i = threadIdx.x; i < nfin; i += WT_THREADS) c += ord2f(s_val[i]) <= lim ? 1 : 0;
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (lane == 0 && c) atomicAdd(&s_cnt, c);
-      __syncthreads();
-      return s_cnt;
-    };
-    t = tc_tau_with_margin(t, 2.f * tc_eps(l2 != 0, qnorm[q], max_norm, d, false), cap, count_le);
+    int c_le;
+    const uint32_t* vals = s_val[warp];
+    t = ord2f(warp_kth_key(k, s_hist[warp], [&](auto f) { for (int i = lane; i < nfin; i += 32) f(vals[i]); }, c_le));
+    t = tc_tau_with_margin(t, 2.f * tc_eps(l2 != 0, qnorm[q], max_norm, d, false), cap,
+                           [&](float lim) { int c = 0; for (int i = lane; i < nfin; i += 32) c += ord2f(vals[i]) <= lim ? 1 : 0; return __reduce_add_sync(0xffffffffu, c); });
   }
-  if (threadIdx.x == 0) { tau[q] = t; redo[q] = 0; }
+  if (lane == 0) tau[q] = t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1153,45 +1146,44 @@ static __global__ void __launch_bounds__(HC_THREADS)
 tc_coarse_select_hybrid_kernel(const float* __restrict__ dense, long long ld, int nrows, const float* __restrict__ qnorm, float max_norm,
                                const float* __restrict__ q, const float* __restrict__ vecs, int d, int k, long long id_offset, int api_scores,
                                long long* out_probes, float* out_raw, int* flags) {
-  __shared__ BlockSelShared S;
+  __shared__ int s_hist[WS_BINS];
   __shared__ int s_rows[HC_MAXW];
   __shared__ uint32_t s_kd[HC_MAXW];
   __shared__ long long s_id[HC_MAXW];
   __shared__ int s_m, s_ns;
-  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qi = blockIdx.x;
-  constexpr int KT = KPT / 4;  // keys per thread: the score row is spread over the 128 threads' registers
-  uint32_t key[KT];
+  if (warp == 0) {
+    uint32_t key[KPT];
 #pragma unroll
-  for (int j = 0; j < KT; ++j) {
-    const int r = threadIdx.x + j * HC_THREADS;
-    key[j] = r < nrows ? f2ord(dense[(size_t)qi * ld + r]) : 0xFFFFFFFFu;
-  }
-  if (threadIdx.x == 0) { s_m = 0; s_ns = 0; }
-  const uint32_t kth = block_kth_key_any(k, S, [&](auto f) {
+    for (int j = 0; j < KPT; ++j) {
+      const int r = lane + j * 32;
+      key[j] = r < nrows ? f2ord(dense[(size_t)qi * ld + r]) : 0xFFFFFFFFu;
+    }
+    int c_le;
+    const uint32_t kth = warp_kth_key(k, s_hist, [&](auto f) {
 #pragma unroll
-    for (int j = 0; j < KT; ++j) if (key[j] != 0xFFFFFFFFu) f(key[j]);
-  });  // (barriers inside: s_m / s_ns are published)
-  {
+      for (int j = 0; j < KPT; ++j) if (key[j] != 0xFFFFFFFFu) f(key[j]);
+    }, c_le);
     const float a_k = ord2f(kth);
     const float two_eps = 2.f * tc_eps(L2, qnorm[qi], max_norm, d, true);
     const uint32_t thr_hi = f2ord(__fadd_ru(a_k, two_eps));
     const uint32_t thr_lo = f2ord(__fsub_rd(a_k, two_eps));
-    const bool set_mode = out_raw == nullptr && S.c_le == k;
+    const bool set_mode = out_raw == nullptr && c_le == k;
+    int ns = 0, m = 0;
 #pragma unroll
-    for (int j = 0; j < KT; ++j) {
-      const int r = threadIdx.x + j * HC_THREADS;
+    for (int j = 0; j < KPT; ++j) {
+      const int r = lane + j * 32;
       const bool in = key[j] <= thr_hi && key[j] != 0xFFFFFFFFu;
       const bool sure = in && set_mode && key[j] <= thr_lo;
       const unsigned ms = __ballot_sync(0xffffffffu, sure), mw = __ballot_sync(0xffffffffu, in && !sure);
       const unsigned lt = (1u << lane) - 1u;
-      int bs = 0, bw = 0;
-      if (lane == 0) { if (ms) bs = atomicAdd(&s_ns, __popc(ms)); if (mw) bw = atomicAdd(&s_m, __popc(mw)); }
-      bs = __shfl_sync(0xffffffffu, bs, 0);
-      bw = __shfl_sync(0xffffffffu, bw, 0);
-      if (sure) out_probes[(size_t)qi * k + bs + __popc(ms & lt)] = r + id_offset;  // (fewer than k certain rows: kth itself is not certain)
-      if (in && !sure) { const int p = bw + __popc(mw & lt); if (p < HC_MAXW) s_rows[p] = r; }
+      if (sure) out_probes[(size_t)qi * k + ns + __popc(ms & lt)] = r + id_offset;
+      if (in && !sure) { const int p = m + __popc(mw & lt); if (p < HC_MAXW) s_rows[p] = r; }
+      ns += __popc(ms);
+      m += __popc(mw);
     }
+    if (lane == 0) { s_m = m; s_ns = ns; }
   }
   __syncthreads();
   const int m = s_m, ns = s_ns;
@@ -1617,7 +1609,7 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   int* redo = S.alloc<int>(nq);
   const size_t tau_smem = (size_t)TAU_PL * 8 + std::max(sel_smem, (size_t)TAU_SORT * 8);
   if (srows == TC_SAMPLE) {  // warp per query; the block kernel only redoes queries with more sampled spans than a warp stages
-    tc_tau_warp_kernel<<<(unsigned)nq, WT_THREADS, 0, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, k, (int)nq, l2 ? 1 : 0, P.qnorm, v.max_norm, d, cap, tau, redo);
+    tc_tau_warp_kernel<<<(unsigned)cdiv(nq, WT_WARPS), WT_WARPS * 32, 0, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, k, (int)nq, l2 ? 1 : 0, P.qnorm, v.max_norm, d, cap, tau, redo);
     tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, tau_smem, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, srows, k, pool, l2 ? 1 : 0, P.qnorm, v.max_norm, d, 0, cap, tau, redo);
   } else {
     tc_tau_kernel<<<(unsigned)nq, SCAN_THREADS, tau_smem, s>>>(probes, P.pos, P.cnt, P.item_off, v.list_len, P.items, nprobe, sample, srows, k, pool, l2 ? 1 : 0, P.qnorm, v.max_norm, d, 1, cap, tau, nullptr);
