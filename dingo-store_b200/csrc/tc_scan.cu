@@ -907,6 +907,26 @@ tc_final_hybrid_kernel(const unsigned long long* __restrict__ cand, const int* _
   if (m > HF_MAXW) { if (threadIdx.x == 0) redo[qi] = 1; return; }
   const int quad = threadIdx.x >> 2, t = threadIdx.x & 3;
   const float* qs = reinterpret_cast<const float*>(s_dyn);
+  if (rows_g <= 0) {
+    // direct form: every in-window row is prefetched towards L2 at once, then 32 quads score 32 rows per round straight from
+    // global memory (no staging buffer: 16 CTAs per SM keep ~500 rows in flight per SM)
+    const int lines = (d * 4 + 127) / 128;
+    for (int i = threadIdx.x; i < m * lines; i += HF_THREADS) {
+      const char* ptr = reinterpret_cast<const char*>(vecs + (size_t)(uint32_t)s_rows[i / lines] * d) + (size_t)(i % lines) * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+    }
+    cp_async_wait_all();  // the query row
+    __syncthreads();
+    for (int base = 0; base < m; base += HF_THREADS / 4) {
+      const int i = base + quad;
+      const bool valid = i < m;
+      const long long row = (long long)(uint32_t)s_rows[valid ? i : 0];
+      const long long id = valid ? ids[row] : -1;
+      const float v = quad_distance<L2>(vecs + (size_t)row * d, qs, d, t, true);
+      if (valid && t == 0) { s_kd[i] = f2ord(L2 ? v : -v); s_id[i] = id; }
+    }
+    __syncthreads();
+  } else {
   unsigned char* stage = s_dyn + pitch;
   for (int g0 = 0; g0 < m; g0 += rows_g) {
     const int ng = min(rows_g, m - g0);
@@ -924,6 +944,7 @@ tc_final_hybrid_kernel(const unsigned long long* __restrict__ cand, const int* _
       if (valid && t == 0) s_kd[g0 + i] = f2ord(L2 ? v : -v);
     }
     __syncthreads();
+  }
   }
   const int have = min(m, k);
   for (int e = threadIdx.x; e < m; e += HF_THREADS) {
@@ -1627,9 +1648,10 @@ void tc_search(IndexBase* ix, const TcView& v, bool l2, int64_t nq, const float*
   const size_t fast_smem = ((size_t)d * 4 + 15) / 16 * 16 + (size_t)FIN_MAXW * 16 + (size_t)cap * 8;
   const int* fin_redo = nullptr;
   const int hf_pitch = d * 4 + 16;  // staged row pitch: 16-byte aligned, rows land on different banks
-  const int hf_rows = std::min(32, std::max(HF_ROW_BYTES, 2 * hf_pitch) / hf_pitch - 1);
+  static const bool hf_direct = !(getenv("B200VS_FINAL_STAGED") && atoi(getenv("B200VS_FINAL_STAGED")) != 0);
+  const int hf_rows = hf_direct ? 0 : std::min(32, std::max(HF_ROW_BYTES, 2 * hf_pitch) / hf_pitch - 1);
   const size_t hsm = (size_t)(hf_rows + 1) * hf_pitch;
-  if (2 * k <= HF_MAXW && hf_rows >= 1 && hsm <= 96 * 1024) {  // warp select + block re-score; the block kernels below only redo queries whose window exceeds HF_MAXW rows
+  if (2 * k <= HF_MAXW && hsm <= 96 * 1024) {  // warp select + block re-score; the block kernels below only redo queries whose window exceeds HF_MAXW rows
     if (l2) tc_final_hybrid_kernel<true><<<(unsigned)nq, HF_THREADS, hsm, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, hf_rows, hf_pitch, out_dist, out_ids, flags, redo);
     else tc_final_hybrid_kernel<false><<<(unsigned)nq, HF_THREADS, hsm, s>>>(cand, cand_cnt, cap, tau, P.qnorm, v.max_norm, q, v.vecs, v.ids, d, k, hf_rows, hf_pitch, out_dist, out_ids, flags, redo);
     fin_redo = redo;
