@@ -37,6 +37,7 @@ struct FsArgs {
   uint32_t* part_kd;     // [nq, nslices, k]
   long long* part_id;    // [nq, nslices, k]
   int* tickets;          // [nq] zeroed before the launch
+  uint32_t* gthr_inv;    // [nq] zeroed: ~(smallest k-th key any slice has published) — an upper bound of the global k-th key
   float* out_dist;       // [nq, k] API semantics
   long long* out_ids;    // [nq, k]
   long long* dbg;        // optional [8] clock64 stamps of slice 0 and of the merging CTA (B200VS_FS_DEBUG)
@@ -62,6 +63,28 @@ struct FsShared {
 template <class Emit>
 __device__ __forceinline__ int fs_topk_block(const uint32_t* kd, const long long* id, int n, int k, FsShared& F, Emit emit) {
   const int lane = threadIdx.x & 31;
+  if (n <= 2 * (int)blockDim.x) {  // few pairs: every thread ranks its pairs against all others — cheaper than any selection pass
+    if (threadIdx.x == 0) F.m = 0;
+    __syncthreads();
+    int live = 0;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const uint32_t d0 = kd[e];
+      const long long i0 = id[e];
+      if (d0 == KEY_SENTINEL_D && i0 == KEY_SENTINEL_ID) continue;
+      ++live;
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const uint32_t dj = kd[j];
+        const long long ij = id[j];
+        rank += (key_less(dj, ij, d0, i0) || (dj == d0 && ij == i0 && j < e)) ? 1 : 0;  // (sentinel pairs rank last)
+      }
+      if (rank < k) emit(rank, d0, i0);
+    }
+    live = __reduce_add_sync(0xffffffffu, live);
+    if (lane == 0 && live) atomicAdd(&F.m, live);
+    __syncthreads();
+    return min(F.m, k);
+  }
   uint32_t kth = 0xFFFFFFFFu;
   if (n > k) kth = block_kth_key_any(k, F.sel, [&](auto f) { for (int i = threadIdx.x; i < n; i += blockDim.x) f(kd[i]); });
   if (threadIdx.x == 0) F.m = 0;
@@ -143,7 +166,10 @@ static __global__ void __launch_bounds__(FS_THREADS) flat_small_kernel(const FsA
   long long* pi = a.part_id + ((size_t)qi * nslices + slice) * k;
   {
     const int n = s_n;
-    const int have = fs_topk_block(s_kd, s_id, n, k, F, [&](int rank, uint32_t kd, long long id) { pk[rank] = kd; pi[rank] = id; });
+    const int have = fs_topk_block(s_kd, s_id, n, k, F, [&](int rank, uint32_t kd, long long id) {
+      pk[rank] = kd; pi[rank] = id;
+      if (rank == k - 1) atomicMax(a.gthr_inv + qi, ~kd);  // this slice alone holds k rows at or below kd: the global k-th key is <= kd
+    });
     for (int i = have + (int)threadIdx.x; i < k; i += FS_THREADS) { pk[i] = KEY_SENTINEL_D; pi[i] = KEY_SENTINEL_ID; }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -160,10 +186,25 @@ static __global__ void __launch_bounds__(FS_THREADS) flat_small_kernel(const FsA
   const int tot = nslices * k;  // <= FS_PAIRS (launcher)
   const uint32_t* allk = a.part_kd + (size_t)qi * nslices * k;
   const long long* alli = a.part_id + (size_t)qi * nslices * k;
-  for (int j = threadIdx.x; j < tot; j += FS_THREADS) { s_kd[j] = __ldcg(allk + j); s_id[j] = __ldcg(alli + j); }  // empty slots carry the sentinel pair
+  // only pairs at or below the tightest published k-th key can be among the global top-k: a few dozen of the nslices * k
+  const uint32_t thr = ~__ldcg(a.gthr_inv + qi);
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (int base = 0; base < tot; base += FS_THREADS) {
+    const int j = base + threadIdx.x;
+    uint32_t kd = KEY_SENTINEL_D;
+    long long id = KEY_SENTINEL_ID;
+    if (j < tot) { kd = __ldcg(allk + j); id = __ldcg(alli + j); }
+    const bool in = kd <= thr && !(kd == KEY_SENTINEL_D && id == KEY_SENTINEL_ID);
+    const unsigned msk = __ballot_sync(0xffffffffu, in);
+    int wbase = 0;
+    if ((threadIdx.x & 31) == 0 && msk) wbase = atomicAdd(&s_n, __popc(msk));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (in) { const int p = wbase + __popc(msk & ((1u << (threadIdx.x & 31)) - 1u)); s_kd[p] = kd; s_id[p] = id; }
+  }
   __syncthreads();
   {
-    const int n = tot;
+    const int n = s_n;
     const int have = fs_topk_block(s_kd, s_id, n, k, F, [&](int rank, uint32_t kd, long long id) {
       const float v = ord2f(kd);
       const float raw = L2 ? v : -v;
@@ -199,11 +240,12 @@ void flat_small_search(IndexBase* ix, bool l2, const float* vecs, const long lon
   a.filt.sorted_ids = sc.sorted_ids_dev; a.filt.n_ids = sc.n_ids;
   a.part_kd = S.alloc<uint32_t>((size_t)nq * nslices * k);
   a.part_id = S.alloc<long long>((size_t)nq * nslices * k);
-  a.tickets = S.alloc<int>(nq);
+  a.tickets = S.alloc<int>(2 * nq);
+  a.gthr_inv = reinterpret_cast<uint32_t*>(a.tickets + nq);
   a.out_dist = out_dist; a.out_ids = out_ids;
   static const bool debug = getenv("B200VS_FS_DEBUG") != nullptr;
   a.dbg = debug ? S.alloc<long long>(8) : nullptr;
-  B200VS_CUDA(cudaMemsetAsync(a.tickets, 0, (size_t)nq * 4, s));
+  B200VS_CUDA(cudaMemsetAsync(a.tickets, 0, (size_t)nq * 8, s));
   const size_t smem = (size_t)FS_PAIRS * 12 + ((size_t)d * 4 + 15) / 16 * 16;
   dim3 grid(nslices, (unsigned)nq);
   if (l2) flat_small_kernel<true><<<grid, FS_THREADS, smem, s>>>(a);

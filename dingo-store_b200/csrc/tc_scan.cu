@@ -486,8 +486,9 @@ template <class CountLE>
 __device__ __forceinline__ float tc_tau_with_margin(float tau, float two_eps, int cap, CountLE count_le) {
   if (count_le(__fsub_rd(tau, two_eps)) >= TAU_SAFE) return tau;
   const float lim = __fadd_ru(tau, two_eps);
-  const long long predicted = (long long)count_le(lim) * (TC_SPAN / TC_SAMPLE);
-  return predicted * 4 <= (long long)cap * 3 ? lim : tau;
+  const float cs = (float)count_le(lim);  // sampled scores under T: the capture count is ~ (cs +- sqrt(cs)) * sampling ratio
+  const float predicted = (cs + 4.f * sqrtf(cs)) * (float)(TC_SPAN / TC_SAMPLE);  // + 4 sigma: thousands of queries per batch
+  return predicted <= (float)cap ? lim : tau;
 }
 
 constexpr int TAU_PL = 4096;  // (sample slot, column) pairs staged per query
@@ -1478,7 +1479,7 @@ static int64_t tc_sample_bound(const TcView& v, int64_t npairs) {  // spans are 
   const int64_t max_spans = (v.max_chunks_per_list + 3) / 4 + 1;
   return (npairs / TC_NQT + 1) * max_spans + (v.total_chunks + 3) / 4 + v.nlist;
 }
-static int tc_cand_cap(int k) { return std::min(16384, std::max(4096, next_pow2(256 * k))); }
+static int tc_cand_cap(int k) { return std::min(16384, std::max(8192, next_pow2(256 * k))); }
 
 // Per-device one-time setup: cudaFuncSetAttribute applies to the CURRENT device only, and one process may hold indexes
 // on several GPUs (b200vs_params.device), so the opt-in shared-memory limits are raised once per device ordinal.
