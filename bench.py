@@ -382,7 +382,7 @@ def main():
     alg_bytes = rows * (d * 4 + 8)
     # DRAM traffic of the same kernel from the committed ncu --set full capture (only for the workload it was taken on)
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "round1", "ncu_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "round2", "ncu_traffic.json")
     if world == 1 and (args.nb, args.dim, args.nlist, args.nprobe, args.batch, args.k) == (1_000_000, 768, 1024, 32, 1024, 10) and os.path.exists(tp):
         try:
             tj = json.load(open(tp))

@@ -26,6 +26,7 @@ IndexBase* make_flat(b200vs_metric m, int d, const b200vs_params& p);
 namespace {
 
 constexpr int KSUB = 256;
+constexpr int PQ_THREADS = 512;  // code-scan CTA: one 96 KB LUT serves 16 warps (2 CTAs per SM -> 32 warps hide the code-load latency)
 
 __device__ __forceinline__ float ip_seq(const float* a, const float* b, int n) {
   float r = 0.f;
@@ -131,7 +132,7 @@ struct PqScanArgs {
 
 // block (split, query): probes split round-robin; LUT in shared memory; one thread per code row
 template <bool L2>
-__global__ void __launch_bounds__(SCAN_THREADS) pq_scan_select_kernel(const PqScanArgs a) {
+__global__ void __launch_bounds__(PQ_THREADS) pq_scan_select_kernel(const PqScanArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* tab = reinterpret_cast<float*>(smem);
   const int M = a.M, T = M * KSUB;
@@ -167,7 +168,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) pq_scan_select_kernel(const PqSc
         if (id >= 0 && filter_pass(a.filt, id)) {
           const unsigned char* code = a.codes + (size_t)row * M;
           float dis = dis0;
-          if ((M & 15) == 0) {
+          if ((M & 15) == 0 && M <= 128) {
+            // all code words of the row first (<= 8 independent 16-byte loads in flight), then the strictly ordered LUT sums
+            uint4 cw[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) if (g * 16 < M) cw[g] = *reinterpret_cast<const uint4*>(code + g * 16);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (g * 16 < M) {
+                const uint32_t w[4] = {cw[g].x, cw[g].y, cw[g].z, cw[g].w};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dis = __fadd_rn(dis, tab[(g * 16 + j) * KSUB + ((w[j >> 2] >> (8 * (j & 3))) & 0xff)]);
+              }
+            }
+          } else if ((M & 15) == 0) {
             for (int m0 = 0; m0 < M; m0 += 16) {
               const uint4 c = *reinterpret_cast<const uint4*>(code + m0);
               const uint32_t w[4] = {c.x, c.y, c.z, c.w};
@@ -466,7 +480,7 @@ struct IvfPqIndex : IndexBase {
     a.codes = codes.p; a.ids = ids.p; a.probes = probes; a.coarse = coarse; a.list_off = L.d_off.p; a.list_len = L.d_len.p;
     a.sim = sim; a.pre = l2 ? pre.p : nullptr; a.M = M; a.nprobe = nprobe; a.k = k;
     a.nsplit = (int)std::max<int64_t>(1, std::min<int64_t>(nprobe, (148 * 2 + nq - 1) / nq));
-    a.pool_cap = select_pool_cap(k, SCAN_THREADS);
+    a.pool_cap = select_pool_cap(k, PQ_THREADS);
     a.has_thr = has_thr ? 1 : 0;
     a.thr_key = has_thr ? f2ord(l2 ? thr_raw : -thr_raw) : 0;
     a.ws_kd = scratch.alloc<uint32_t>((size_t)nq * a.nsplit * k);
@@ -480,13 +494,13 @@ struct IvfPqIndex : IndexBase {
     ScopedKernelTimer timer(this, s, profiling);
     if (l2) {
       B200VS_CUDA(cudaFuncSetAttribute(pq_scan_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      pq_scan_select_kernel<true><<<grid, SCAN_THREADS, smem, s>>>(a);
+      pq_scan_select_kernel<true><<<grid, PQ_THREADS, smem, s>>>(a);
       timer.stop();
       B200VS_CUDA(cudaFuncSetAttribute(merge_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       merge_select_kernel<true><<<(unsigned)nq, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, a.nsplit, k, a.pool_cap, od, nullptr, oi, oc, nullptr, nullptr);
     } else {
       B200VS_CUDA(cudaFuncSetAttribute(pq_scan_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      pq_scan_select_kernel<false><<<grid, SCAN_THREADS, smem, s>>>(a);
+      pq_scan_select_kernel<false><<<grid, PQ_THREADS, smem, s>>>(a);
       timer.stop();
       B200VS_CUDA(cudaFuncSetAttribute(merge_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       merge_select_kernel<false><<<(unsigned)nq, SCAN_THREADS, smem2, s>>>(a.ws_kd, a.ws_kid, a.nsplit, k, a.pool_cap, od, nullptr, oi, oc, nullptr, nullptr);
