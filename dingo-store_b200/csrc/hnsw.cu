@@ -595,6 +595,18 @@ struct HnswIndex : IndexBase {
     const int64_t* hdr = (const int64_t*)base;
     if (hdr[0] != 0x57534E48 || hdr[2] != dim || hdr[3] != (int64_t)G.M) fail(B200VS_EILLEGAL_PARAMETERS, "bad HNSW state blob");
     const int64_t n = hdr[1];
+    {  // the blob must hold every section BEFORE anything is copied out of it
+      if (n < 0 || n > (1LL << 31)) fail(B200VS_EILLEGAL_PARAMETERS, "bad HNSW state blob (row count)");
+      auto pad8 = [](uint64_t v) { return (v + 7) / 8 * 8; };
+      uint64_t need = pad8(64 + (uint64_t)n * 4) + (uint64_t)(n + 1) * 8;
+      if (len < need) fail(B200VS_EILLEGAL_PARAMETERS, "state blob truncated");
+      const int64_t* off_chk = (const int64_t*)((const char*)blob + pad8(64 + (uint64_t)n * 4));
+      const int64_t up = off_chk[n];
+      if (up < 0 || up > (int64_t)(len / 4)) fail(B200VS_EILLEGAL_PARAMETERS, "bad HNSW state blob (link pool)");
+      need = pad8(need + (uint64_t)n * (2 * G.M + 1) * 4 + (uint64_t)up * 4);
+      need = pad8(need + (uint64_t)n * dim * 4) + (uint64_t)n * 8;
+      if (len < need) fail(B200VS_EILLEGAL_PARAMETERS, "state blob truncated");
+    }
     HostGraph H;
     H.init(metric, dim, (int)G.M, (int)G.efc, 100);
     H.reserve(std::max<int64_t>(n, 1));
@@ -661,7 +673,7 @@ struct HnswIndex : IndexBase {
   }
   // hnswlib getDataByLabel (hnsw.cc:383-395): the stored (for cosine: normalised) vector of a live label
   void reconstruct(int64_t n, const int64_t* in_ids, float* out, uint8_t* found) override {
-    std::shared_lock<std::shared_mutex> rl(rw);
+    RwSharedGuard rl(this);
     for (int64_t i = 0; i < n; ++i) {
       auto it = G.lookup.find(in_ids[i]);
       const bool ok = it != G.lookup.end() && !G.deleted[it->second];
@@ -755,7 +767,7 @@ struct HnswIndex : IndexBase {
     return (int64_t)(G.n * ((G.maxM0 + 1) * 4 + (int64_t)dim * 4 + 8));  // hnsw.cc:612-623: per-element level-0 block
   }
   void export_lists(int64_t* list_off, float* vectors, uint8_t*, int64_t* out_ids) override {
-    std::shared_lock<std::shared_mutex> rl(rw);
+    RwSharedGuard rl(this);
     int64_t o = 0;
     for (int64_t i = 0; i < G.n; ++i) {
       if (G.deleted[i]) continue;
@@ -766,7 +778,7 @@ struct HnswIndex : IndexBase {
     if (list_off) { list_off[0] = 0; list_off[1] = o; }
   }
   int64_t get_state(void* blob, size_t cap) override {
-    std::shared_lock<std::shared_mutex> rl(rw);
+    RwSharedGuard rl(this);
     const int64_t n = G.n;
     int64_t up = 0;
     for (int64_t i = 0; i < n; ++i) up += (int64_t)G.linkup[i].size();

@@ -15,6 +15,7 @@ namespace b200vs {
 thread_local std::string g_last_error;
 thread_local Lane* IndexBase::tl_lane = nullptr;
 thread_local IndexBase* IndexBase::tl_owner = nullptr;
+thread_local const IndexBase* RwSharedGuard::tl_held = nullptr;
 
 LaneGuard::LaneGuard(IndexBase* ix_, cudaStream_t s) : ix(ix_), lane(nullptr), prev_owner(IndexBase::tl_owner), prev_lane(IndexBase::tl_lane), stream(s) {
   const bool own = s == nullptr;  // host-pointer / NULL-stream call: runs on the lane's own stream
@@ -116,6 +117,7 @@ void rd(FILE* f, void* p, size_t n) { if (n && fread(p, 1, n, f) != n) fail(B200
 }  // namespace
 
 void IndexBase::save(const std::string& path) {
+  RwSharedGuard hold(this);  // one reader hold across count / trained state / export: no add can slip in between
   const int64_t st_len = get_state(nullptr, 0);
   std::vector<unsigned char> st((size_t)std::max<int64_t>(st_len, 0));
   if (st_len > 0) get_state(st.data(), st.size());
@@ -148,6 +150,15 @@ void IndexBase::load(const std::string& path) {
     if (memcmp(h.magic, "B2VSIDX1", 8) != 0 || h.type != (int)type || h.metric != (int)metric || h.dim != dim)
       fail(B200VS_EINTERNAL, "index file does not match this index (type / metric / dimension)");
     if (count() != 0) fail(B200VS_EINTERNAL, "load into a non-empty index");
+    {  // the header's sizes must fit the file before anything is allocated from them
+      const long here = ftell(f);
+      fseek(f, 0, SEEK_END);
+      const long fsize = ftell(f);
+      fseek(f, here, SEEK_SET);
+      const double need = (double)h.state_len + ((double)h.nlist + 1) * 8 + (double)h.count * (8 + (double)dim * 4);
+      if (h.state_len < 0 || h.count < 0 || h.nlist < 0 || h.nlist > (1 << 24) || need > (double)(fsize - here))
+        fail(B200VS_EINTERNAL, "corrupt index file (header sizes exceed the file)");
+    }
     std::vector<unsigned char> st((size_t)h.state_len);
     rd(f, st.data(), st.size());
     if (h.state_len > 0) set_state(st.data(), st.size());
@@ -356,7 +367,7 @@ struct FlatIndex : IndexBase {
   }
 
   void reconstruct(int64_t n, const int64_t* in_ids, float* out, uint8_t* found) override {
-    std::shared_lock<std::shared_mutex> rl(rw);
+    RwSharedGuard rl(this);
     std::lock_guard<std::mutex> gl(gpu_mu);
     set_device();
     for (int64_t i = 0; i < n; ++i) {
@@ -372,7 +383,7 @@ struct FlatIndex : IndexBase {
   int64_t memory_size() const override { return (int64_t)(vecs.cap * 4 + ids.cap * 8 + norms.cap * 4); }
 
   void export_lists(int64_t* list_off, float* vectors, uint8_t*, int64_t* out_ids) override {
-    std::shared_lock<std::shared_mutex> rl(rw);
+    RwSharedGuard rl(this);
     std::lock_guard<std::mutex> gl(gpu_mu);
     set_device();
     const int64_t live = rows - ndeleted;
@@ -471,7 +482,7 @@ struct IvfFlatIndex : IndexBase {
     install_centroids((const float*)((const char*)blob + 32), k);
   }
   int64_t get_state(void* blob, size_t cap) override {
-    std::shared_lock<std::shared_mutex> rl(rw);
+    RwSharedGuard rl(this);
     if (!trained) return 0;
     const size_t need = 32 + (size_t)nlist * dim * 4;
     if (!blob || cap < need) return (int64_t)need;
@@ -841,7 +852,7 @@ void IvfFlatIndex::range_search_dev(int64_t nq, const float* xq, float radius, i
 }
 
 void IvfFlatIndex::export_lists(int64_t* list_off, float* vectors, uint8_t*, int64_t* out_ids) {
-  std::shared_lock<std::shared_mutex> rl(rw);
+  RwSharedGuard rl(this);
   std::lock_guard<std::mutex> gl(gpu_mu);
   set_device();
   std::vector<float> rowbuf;
@@ -866,7 +877,7 @@ void IvfFlatIndex::export_lists(int64_t* list_off, float* vectors, uint8_t*, int
 }
 
 int64_t IvfFlatIndex::export_list(int list, int64_t cap, float* vectors, int64_t* out_ids) {
-  std::shared_lock<std::shared_mutex> rl(rw);
+  RwSharedGuard rl(this);
   std::lock_guard<std::mutex> gl(gpu_mu);
   if (list < 0 || list >= nlist) fail(B200VS_EILLEGAL_PARAMETERS, "list id out of range");
   set_device();

@@ -284,6 +284,22 @@ struct IndexBase {
   void launch_count(int n = 1) { stats[0] += n; }
 };
 
+// Shared (reader) hold of an index's rw lock that composes: an operation made of several locked steps (Save = count, then
+// trained state, then list export) takes it once at the top, the steps' own guards then see the hold and do not lock again
+// (re-acquiring a std::shared_mutex in shared mode can dead-lock behind a queued writer, and releasing it between the steps
+// lets an add grow the index past the buffers sized from the earlier count).
+struct RwSharedGuard {
+  static thread_local const IndexBase* tl_held;
+  const IndexBase* prev;
+  std::shared_lock<std::shared_mutex> lk;
+  explicit RwSharedGuard(IndexBase* ix) : prev(tl_held) {
+    if (tl_held != ix) { lk = std::shared_lock<std::shared_mutex>(ix->rw); tl_held = ix; }
+  }
+  ~RwSharedGuard() { tl_held = prev; }
+  RwSharedGuard(const RwSharedGuard&) = delete;
+  RwSharedGuard& operator=(const RwSharedGuard&) = delete;
+};
+
 // RAII: pick a lane for a search on stream `s` (nullptr = a lane-owned stream), lock it, make it the thread's scratch
 struct LaneGuard {
   IndexBase* ix;

@@ -264,7 +264,7 @@ struct IvfPqIndex : IndexBase {
     install(f, f + nc);
   }
   int64_t get_state(void* blob, size_t cap) override {
-    std::shared_lock<std::shared_mutex> rl(rw);
+    RwSharedGuard rl(this);
     if (mode != kIvfPq) return 0;
     const size_t nc = (size_t)nlist * dim, ncb = (size_t)M * KSUB * (dim / M);
     const size_t need = 48 + (nc + ncb) * 4;
@@ -303,6 +303,7 @@ struct IvfPqIndex : IndexBase {
       }
     }
     std::unique_lock<std::shared_mutex> wl(rw);
+    if (mode != kNone) return;  // another caller trained while the lock was released
     std::lock_guard<std::mutex> gl(gpu_mu);
     set_device();
     quiesce();
@@ -538,6 +539,7 @@ struct IvfPqIndex : IndexBase {
   // container "B2VSPQ01" = mode, then either the inner Flat index's rows or {trained-state blob, list offsets, ids,
   // PQ codes in list-major order}.  Codes are restored as stored (never re-encoded: the vectors are gone).
   void save(const std::string& path) override {
+    RwSharedGuard hold(this);  // one reader hold across count / trained state / export
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) fail(B200VS_EINTERNAL, "cannot open " + path);
     auto wr = [&](const void* p, size_t n) { if (n && fwrite(p, 1, n, f) != n) fail(B200VS_EINTERNAL, "short write"); };
@@ -618,7 +620,7 @@ struct IvfPqIndex : IndexBase {
 
   void export_lists(int64_t* list_off, float* vectors, uint8_t* out_codes, int64_t* out_ids) override {
     if (mode == kFlat) { flat->export_lists(list_off, vectors, out_codes, out_ids); return; }
-    std::shared_lock<std::shared_mutex> rl(rw);
+    RwSharedGuard rl(this);
     std::lock_guard<std::mutex> gl(gpu_mu);
     set_device();
     std::vector<unsigned char> buf;
