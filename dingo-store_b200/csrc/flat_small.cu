@@ -63,7 +63,7 @@ struct FsShared {
 template <class Emit>
 __device__ __forceinline__ int fs_topk_block(const uint32_t* kd, const long long* id, int n, int k, FsShared& F, Emit emit) {
   const int lane = threadIdx.x & 31;
-  if (n <= 2 * (int)blockDim.x) {  // few pairs: every thread ranks its pairs against all others — cheaper than any selection pass
+  if (n <= FS_CT) {  // a handful of pairs (the pruned merge): every thread ranks its pair against all others — n^2 compares, only worth it when tiny
     if (threadIdx.x == 0) F.m = 0;
     __syncthreads();
     int live = 0;
