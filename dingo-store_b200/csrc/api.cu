@@ -269,15 +269,16 @@ void run_coalesced(IndexBase* ix, std::vector<CoalesceReq*>& batch) {
   int64_t total = 0;
   for (auto* r : batch) total += r->nq;
   const int k = batch[0]->k, d = ix->dim;
-  // pinned staging owned by the process-wide pool of this index: queries in, results out (one H2D, one D2H of each kind)
+  // pinned staging owned by the calling (leader) thread: queries in, results out (one H2D, one D2H of each kind)
   const size_t qbytes = (size_t)total * d * 4, dbytes = (size_t)total * k * 4, ibytes = (size_t)total * k * 8;
   const size_t need = qbytes + dbytes + ibytes + 64;
   static thread_local void* pin = nullptr;
   static thread_local size_t pin_cap = 0;
   if (pin_cap < need) {
+    ix->set_device();
     if (pin) cudaFreeHost(pin);
     pin = nullptr; pin_cap = 0;
-    B200VS_CUDA(cudaHostAlloc(&pin, need * 2, cudaHostAllocDefault));
+    B200VS_CUDA(cudaHostAlloc(&pin, need * 2, cudaHostAllocPortable));  // portable: the calling thread may serve indexes on several devices
     pin_cap = need * 2;
   }
   float* hq = reinterpret_cast<float*>(pin);
