@@ -160,6 +160,24 @@ static void test_hnsw() {
   sp.mutable_hnsw()->set_efsearch(0);
   EXPECT(ix->RangeSearch({vs[0]}, 1.0f, {}, false, sp, results).error_code() == pb::error::EVECTOR_NOT_SUPPORT);
   EXPECT(!ix->IsExceedsMaxElements(10) && ix->IsExceedsMaxElements(100000));
+  // reconstruct (vector_index_hnsw.cc:383-395): cosine never returns vectors (:469-472) ...
+  results.clear();
+  EXPECT(ix->Search({vs[0]}, 3, {}, true, sp, results).ok());
+  EXPECT(results.size() == 1 && results[0].vector_with_distances(0).vector_with_id().vector().float_values_size() == 0);
+  // ... an L2 index returns the stored vector of every hit
+  auto l2 = make(pb::common::VECTOR_INDEX_TYPE_HNSW, pb::common::METRIC_TYPE_L2, d, 0, 2);
+  EXPECT(l2->Upsert(vs).ok());
+  results.clear();
+  EXPECT(l2->Search({vs[3]}, 2, {}, true, sp, results).ok());
+  EXPECT(results.size() == 1 && results[0].vector_with_distances_size() == 2);
+  if (results.size() == 1 && results[0].vector_with_distances_size() == 2) {
+    const auto& hit = results[0].vector_with_distances(0).vector_with_id();
+    EXPECT(hit.id() == 4 && hit.vector().float_values_size() == d);
+    bool same = hit.vector().float_values_size() == d;
+    for (int j = 0; same && j < d; ++j) same = hit.vector().float_values()[j] == x[(size_t)3 * d + j];
+    EXPECT(same);
+  }
+  EXPECT(l2->VectorIndexSubType() == pb::common::VECTOR_INDEX_TYPE_NONE);  // base default, vector_index.h:238
 }
 
 static void test_calc_distance() {  // the contract of VectorIndexUtils::CalcDistanceEntry (vector_index_utils.cc:48-124)
