@@ -1,11 +1,13 @@
-// warp_select.cuh — warp-level selection primitives: one warp finishes one query with no block barrier.
+// warp_select.cuh — selection primitives of the per-query finish kernels (threshold, window select, coarse probe selection,
+// tiny-batch top-k): the GPU form of the per-query heaps of the reference path (faiss HeapBlockResultHandler behind
+// IndexIVF::search, src/vector/vector_index_ivf_flat.cc:247-251).
 //
-// The per-query finish work of the tile path (capture threshold, window select + exact re-score, coarse probe
-// selection) handles a few hundred keys per query.  A 256-thread CTA per query spends its time in __syncthreads
-// (radix passes, bitonic stages); a warp does the same selection with shuffles / ballots and a warp-private
-// shared-memory histogram, so an SM keeps dozens of queries in flight and a launch over N x 1024 queries (list-sharded
-// ranks finish every query of the global batch) costs about one wave.  These are the GPU form of the per-query heaps of
-// the reference path (faiss HeapBlockResultHandler behind IndexIVF::search, src/vector/vector_index_ivf_flat.cc:247-251).
+// Two forms of the same range-normalised radix select:
+//   warp_kth_key       one warp, shuffles / ballots + a warp-private histogram, no block barrier.  Right when the keys sit in
+//                      the warp's registers or a small staged array (<= ~1024 keys: threshold and coarse kernels).
+//   block_kth_key_any  all threads of the CTA feed one shared histogram.  Right as soon as a CTA owns the query anyway: a lone
+//                      warp executes dependent selection code at ~25 ns per instruction (nothing hides its latencies).
+// Each kernel uses the form that measured faster (profiles/round2/README.md).
 #pragma once
 #include "common.cuh"
 
@@ -63,24 +65,6 @@ __device__ __forceinline__ uint32_t warp_kth_key(int k, int* hist, ForEach for_e
     kk = nk;
     __syncwarp();
     if (shift == 0) { c_le = cle; return lo; }
-  }
-}
-
-// Rank sort of m <= 64 (key, id) pairs held in warp-private shared memory: returns through `emit(rank, index)` for
-// every entry (rank = position in ascending (key, id) order; equal pairs keep their index order).
-template <class Emit>
-__device__ __forceinline__ void warp_rank_sort(const uint32_t* kd, const long long* kid, int m, Emit emit) {
-  const int lane = threadIdx.x & 31;
-  for (int e = lane; e < m; e += 32) {
-    const uint32_t d0 = kd[e];
-    const long long i0 = kid[e];
-    int rank = 0;
-    for (int j = 0; j < m; ++j) {
-      const uint32_t dj = kd[j];
-      const long long ij = kid[j];
-      rank += (key_less(dj, ij, d0, i0) || (dj == d0 && ij == i0 && j < e)) ? 1 : 0;
-    }
-    emit(rank, e);
   }
 }
 
