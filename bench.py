@@ -54,9 +54,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exact-only", action="store_true", help="force the exact FP32 scan path")
-    ap.add_argument("--in-flight", type=int, default=4, help="batches in flight (streams / caller threads); the reference serves "
-                    "searches from a 16-thread pool, so concurrent batches are the deployed shape (measured: 2 -> 1.39 M, "
-                    "3 -> 1.44 M, 4 -> 1.47 M, 8 -> 1.49 M QPS)")
+    ap.add_argument("--in-flight", type=int, default=0, help="batches in flight (streams / caller threads); 0 = 8 on one GPU, 4 per rank "
+                    "when sharded (one NCCL communicator per batch in flight).  The reference serves searches from a 16-thread pool, "
+                    "so concurrent batches are the deployed shape (round-1 sweep: 2 -> 1.39 M, 3 -> 1.44 M, 4 -> 1.47 M, 8 -> 1.49 M QPS)")
     ap.add_argument("--verify", type=int, default=256, help="multi-GPU: queries answered by the sharded path AND by the CPU oracle on every rank's shard")
     return ap.parse_args()
 
@@ -201,6 +201,8 @@ def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.in_flight <= 0:
+        args.in_flight = 8 if world == 1 else 4
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
