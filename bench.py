@@ -6,8 +6,8 @@ batch = 1024 queries per GPU, top-10 — BASELINE.json configs[1] at the batch s
 A "step" is one batched search (b200vs_search) over synthetic U[0,1) vectors.
 
   value : QPS with queries / results resident in HBM (b200vs_search_device), CUDA events, max over ranks.
-  e2e   : QPS through the host-pointer C-ABI call (b200vs_search) with pinned host buffers: H2D of the queries
-          and D2H of (dist, id) inside the timed region.
+  e2e   : QPS through the host-pointer C-ABI call (b200vs_search; b200vs_shard_search when sharded) with pinned host
+          buffers: H2D of the queries and D2H of (dist, id) inside the timed region, one caller thread per batch in flight.
   roofline : the list-scan kernel's algorithmic bytes (rows of the distinct probed lists x (d*4+8))
           / its CUDA-event duration (library profiling mode, separate pass) vs MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline : the CPU oracle (restated reference path, AVX-512 order) on the box's host cores, bounded sample.
