@@ -223,3 +223,29 @@ def test_hnsw_reference_hand_written_rows(oracle):
     hit = I >= 0
     assert hit[:, 0].all() and len(set(I[0][hit[0]].tolist())) == int(hit[0].sum()) and np.abs(D[hit]).max() < 1e-5
     h.close()
+
+
+def test_hnsw_import_adopts_an_exported_graph(oracle):
+    """oracle_hnsw_import: a graph exported by one oracle (or by the engine, same layout) and adopted by a fresh one is searched
+    identically — the mechanism behind parity runs on graphs built by concurrent writers (not reproducible by re-insertion)."""
+    import oracle_lib
+    rng = np.random.default_rng(21)
+    n, d, M, efc = 1500, 24, 8, 60
+    xb = rng.random((n, d)).astype(np.float32)
+    labels = np.arange(10, 10 + n, dtype=np.int64)
+    for metric in (oracle_lib.L2, oracle_lib.COSINE):
+        a = oracle_lib.OracleHnsw(oracle, metric, d, n, M, efc)
+        a.add(xb, labels)
+        blob = a.export()
+        b = oracle_lib.OracleHnsw(oracle, metric, d, n, M, efc)
+        b.load(blob)
+        assert np.array_equal(b.export(), blob)
+        xq = rng.random((30, d)).astype(np.float32)
+        Da, Ia, nda, nha = a.search(xq, 7, ef=40, nthreads=2)
+        Db, Ib, ndb, nhb = b.search(xq, 7, ef=40, nthreads=2)
+        assert np.array_equal(Ia, Ib) and np.array_equal(Da.view(np.uint32), Db.view(np.uint32))
+        assert np.array_equal(nda, ndb) and np.array_equal(nha, nhb)
+        # a blob of another shape is refused
+        c = oracle_lib.OracleHnsw(oracle, metric, d + 8, n, M, efc)
+        with pytest.raises(AssertionError):
+            c.load(blob)
