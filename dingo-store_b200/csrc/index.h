@@ -171,7 +171,9 @@ struct IndexBase {
     Scratch::Mark mark() { return ix->cur().s.mark(); }
     void release(const Scratch::Mark& m) { ix->cur().s.release(m); }
   } scratch{this};
-  int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // counters of the LAST search; several lanes may search at once, so they are relaxed atomics (the values of two
+  // overlapping searches interleave — they are diagnostics — but there is no data race)
+  std::atomic<int64_t> stats[8] = {};
   // profiling only (one caller at a time): CUDA-event marks between the phases of a search, b200vs_last_phase_times
   enum Phase { PH_COARSE_PREP = 0, PH_COARSE_SCAN, PH_COARSE_FINAL, PH_PLAN, PH_SAMPLE, PH_TAU, PH_CAPTURE, PH_FINAL, PH_FALLBACK, PH_OTHER, PH_COMM, PH_MERGE, PH_COUNT };
   float phase_ms[PH_COUNT] = {0};
@@ -195,7 +197,7 @@ struct IndexBase {
     for (auto& m : phase_marks) cudaEventDestroy(m.second);
     phase_marks.clear();
   }
-  void reset_stats() { for (auto& v : stats) v = 0; for (auto& v : phase_ms) v = 0.f; }
+  void reset_stats() { for (auto& v : stats) v.store(0, std::memory_order_relaxed); if (profiling) for (auto& v : phase_ms) v = 0.f; }
   bool profiling = false;  // b200vs_set_profiling: time the dominant scan kernel with CUDA events
   bool loading = false;    // Load(): rows come back exactly as stored (already normalised for cosine)
   virtual int export_nlist() const { return 1; }

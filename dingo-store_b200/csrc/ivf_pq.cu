@@ -453,7 +453,7 @@ struct IvfPqIndex : IndexBase {
       std::shared_lock<std::shared_mutex> rl(flat->rw);
       LaneGuard lg(flat.get(), s);
       flat->search_dev(nq, xq, k, sc, od, oi, s);  // (an id-list filter lives in the outer lane's scratch: same stream, still locked)
-      for (int i = 0; i < 8; ++i) stats[i] = flat->stats[i];
+      for (int i = 0; i < 8; ++i) stats[i] = flat->stats[i].load();
       return;
     }
     scan_codes(nq, xq, k, sc, false, 0.f, od, oi, nullptr, s);
