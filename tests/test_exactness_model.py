@@ -153,3 +153,30 @@ def test_model_has_teeth_window_of_one_eps_is_not_enough():
         if not np.array_equal(exact_topk(e[win], ids[win], k), exact_topk(e, ids, k)):
             misses += 1
     assert misses > 0
+
+
+def test_capture_threshold_rule_failure_rate_and_cost():
+    """tc_tau_with_margin (csrc/tc_scan.cu): T = tau when at least 3 sampled scores lie below tau - 2 eps, else T = tau + 2 eps.
+    Monte Carlo on the headline shape (31 250 probed rows per query, 1 / 64 sampled, k = 10, 2 eps = 0.32 sigma of the score
+    distribution): the rule must (a) almost never leave a query uncertified (A_k + 2 eps > T), while round 1's T = tau alone
+    fails a few times per thousand queries, and (b) capture far fewer rows than the unconditional margin."""
+    rng = np.random.default_rng(5)
+    n, k, ratio, two_eps, trials = 31250, 10, 64, 0.32, 3000
+    fail_rule = fail_tau = 0
+    cap_rule = cap_tau = cap_margin = 0
+    for _ in range(trials):
+        a = rng.standard_normal(n)
+        s = a[::ratio]  # the sampled rows (any fixed subset of iid rows)
+        tau = np.partition(s, k - 1)[k - 1]
+        a_k = np.partition(a, k - 1)[k - 1]
+        c_lo = int((s <= tau - two_eps).sum())
+        T = tau if c_lo >= 3 else tau + two_eps
+        fail_rule += a_k + two_eps > T
+        fail_tau += a_k + two_eps > tau
+        cap_rule += int((a <= T).sum())
+        cap_tau += int((a <= tau).sum())
+        cap_margin += int((a <= tau + two_eps).sum())
+    assert fail_rule / trials <= 1e-3, fail_rule
+    assert fail_rule <= fail_tau
+    assert cap_rule < 0.75 * cap_margin  # the conditional rule is much cheaper than "always add 2 eps"
+    assert cap_rule < 2.2 * cap_tau       # ... and costs at most about twice the captures of the tightest threshold
