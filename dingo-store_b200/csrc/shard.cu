@@ -584,6 +584,35 @@ int b200vs_shard_add(b200vs_shard* h, int64_t n, const float* x, const int64_t* 
   });
 }
 
+// Collective delete (VectorIndexIvfFlat::Delete, vector_index_ivf_flat.cc:162-189, over all shards): every rank passes the same
+// id list and drops the rows it holds; the removed counts are summed over the ranks.  "remove not found vector id" ->
+// EVECTOR_INVALID only when NO rank held any of the ids (:180-184).  Upsert of a sharded index = this call (a not-found
+// status ignored), then b200vs_shard_add*: the new row may live on another rank than the old one.
+int b200vs_shard_remove_ids(b200vs_shard* h, int64_t n, const int64_t* ids, int64_t* n_removed) {
+  return guarded([&]() -> int {
+    b200vs_shard* sh = get(h);
+    if (n_removed) *n_removed = 0;
+    if (n <= 0) return B200VS_OK;  // "delete_ids.empty() -> OK"
+    if (!ids) fail(B200VS_EILLEGAL_PARAMETERS, "null ids");
+    std::lock_guard<std::mutex> g(sh->add_mu);
+    IndexBase* ix = sh->ix;
+    const int64_t local = ix->remove(n, ids);  // -1: untrained (OK, nothing to do)
+    long long tot[2] = {local > 0 ? (long long)local : 0, local < 0 ? 1 : 0};
+    if (sh->world > 1) {
+      ix->set_device();
+      DevBuf<long long> d;
+      d.reserve(2, 0, sh->ws);
+      B200VS_CUDA(cudaMemcpyAsync(d.p, tot, 16, cudaMemcpyHostToDevice, sh->ws));
+      B200VS_NCCL(nccl().AllReduce(d.p, d.p, 2, ncclInt64, ncclSum, sh->lanes[0]->comm, sh->ws));
+      B200VS_CUDA(cudaMemcpyAsync(tot, d.p, 16, cudaMemcpyDeviceToHost, sh->ws));
+      B200VS_CUDA(cudaStreamSynchronize(sh->ws));
+    }
+    if (n_removed) *n_removed = tot[0];
+    if (tot[0] == 0 && tot[1] == 0) fail(B200VS_EVECTOR_INVALID, "remove not found vector id");
+    return B200VS_OK;
+  });
+}
+
 // Bulk builds of large shards: first pass every chunk through plan_add (assignment only, rows are NOT stored), then
 // plan_commit all-reduces the per-list counts and pre-sizes the owned lists in one arena allocation; the second pass
 // (b200vs_shard_add*) then never relocates a list or re-allocates the arena.

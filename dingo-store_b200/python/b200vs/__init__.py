@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "b200vs_last_error", "b200vs_version",
     "b200vs_add_with_ids_device", "b200vs_assign_device", "b200vs_reserve_lists", "b200vs_export_list", "b200vs_set_coalescing", "b200vs_reconstruct", "b200vs_sub_type",
     "b200vs_shard_unique_id", "b200vs_shard_create", "b200vs_shard_destroy", "b200vs_shard_list_range", "b200vs_shard_train",
-    "b200vs_shard_broadcast_state", "b200vs_shard_add", "b200vs_shard_add_device", "b200vs_shard_plan_add_device",
+    "b200vs_shard_broadcast_state", "b200vs_shard_add", "b200vs_shard_add_device", "b200vs_shard_remove_ids", "b200vs_shard_plan_add_device",
     "b200vs_shard_plan_commit", "b200vs_shard_search", "b200vs_shard_search_device",
 ]
 
@@ -115,6 +115,7 @@ def lib():
     L.b200vs_shard_broadcast_state.argtypes = [vp, i32]
     L.b200vs_shard_add.argtypes = [vp, i64, vp, vp]
     L.b200vs_shard_add_device.argtypes = [vp, i64, vp, vp]
+    L.b200vs_shard_remove_ids.argtypes = [vp, i64, vp, ctypes.POINTER(i64)]
     L.b200vs_shard_plan_add_device.argtypes = [vp, i64, vp]
     L.b200vs_shard_plan_commit.argtypes = [vp]
     L.b200vs_shard_search.argtypes = [vp, i64, i64, vp, i32, ctypes.POINTER(SearchParams), vp, vp]
@@ -379,6 +380,13 @@ class Shard:
 
     def add_device(self, n, x_dev_ptr, ids_dev_ptr):
         _check(lib().b200vs_shard_add_device(self.h, n, x_dev_ptr, ids_dev_ptr))
+
+    def delete(self, ids):
+        """Collective delete: every rank passes the same ids; returns the rows removed over all ranks."""
+        ids = _i64(ids)
+        n = ctypes.c_int64(0)
+        _check(lib().b200vs_shard_remove_ids(self.h, ids.size, ids.ctypes.data if ids.size else None, ctypes.byref(n)))
+        return n.value
 
     def plan_add_device(self, n, x_dev_ptr):
         _check(lib().b200vs_shard_plan_add_device(self.h, n, x_dev_ptr))

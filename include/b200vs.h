@@ -203,6 +203,10 @@ int b200vs_shard_train(b200vs_shard* shard, int64_t n, const float* x);
 int b200vs_shard_broadcast_state(b200vs_shard* shard, int32_t root);
 int b200vs_shard_add(b200vs_shard* shard, int64_t n, const float* x, const int64_t* ids);
 int b200vs_shard_add_device(b200vs_shard* shard, int64_t n, const float* x_dev, const int64_t* ids_dev);
+/* collective Delete: every rank passes the same ids; *n_removed = rows removed over all ranks; EVECTOR_INVALID when no rank held
+ * any of them (vector_index_ivf_flat.cc:180-184).  shard_add* appends (IndexIVFFlat::add_with_ids); an Upsert is this call (a
+ * not-found status ignored) followed by shard_add*. */
+int b200vs_shard_remove_ids(b200vs_shard* shard, int64_t n, const int64_t* ids, int64_t* n_removed);
 int b200vs_shard_plan_add_device(b200vs_shard* shard, int64_t n, const float* x_dev);
 int b200vs_shard_plan_commit(b200vs_shard* shard);
 int b200vs_shard_search(b200vs_shard* shard, int64_t seq, int64_t nq, const float* xq, int32_t k, const b200vs_search_params* sp,

@@ -96,6 +96,15 @@ def main():
         note(rank, "threaded calls done")
         # 4) filters travel with the call
         D4, I4 = sh.search(xq, k, seq=9, nprobe=nprobe, id_range=(5, n_per + 7))
+        # 5) collective delete: the same ids on every rank, rows dropped wherever they live; unknown ids -> EVECTOR_INVALID
+        dead = np.concatenate([np.arange(1, 1 + n_per, 7, dtype=np.int64) + r * n_per for r in range(world)])
+        removed = sh.delete(dead)
+        D5, I5 = sh.search(xq, k, seq=10, nprobe=nprobe)
+        try:
+            sh.delete(np.array([-12345], dtype=np.int64))
+            not_found_ok = False
+        except b200vs.B200VSError as e:
+            not_found_ok = e.code == b200vs.EVECTOR_INVALID
         if rank == 0:
             g_off = np.zeros(nlist + 1, np.int64)
             gx, gi = [], []
@@ -119,6 +128,13 @@ def main():
             for sq, (D, I) in res.items():
                 same(D, I, Do, Io, f"threaded call seq {sq}")
             same(D4, I4, Df, If, "filtered call")
+            if removed != dead.size or not not_found_ok:
+                failures.append(f"metric {metric}: collective delete removed {removed} of {dead.size}, not-found status ok = {not_found_ok}")
+            keep = ~np.isin(gi, dead)
+            k_off = np.zeros(nlist + 1, np.int64)
+            k_off[1:] = np.cumsum([int(keep[g_off[l]:g_off[l + 1]].sum()) for l in range(nlist)])
+            Dd, Id = o.ivfflat_search(om, cent, k_off, gx[keep], gi[keep], qn, k, nprobe, nthreads=16)
+            same(D5, I5, Dd, Id, "search after the collective delete")
         sh.close()
         ix.close()
         dist.barrier()
